@@ -1,0 +1,124 @@
+"""ctypes binding of libgpk.so (include/gpk.h).  There is NO CPU fallback: if the CUDA library
+cannot be loaded the product path raises, and every numeric call needs a CUDA device."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+GPK_F32, GPK_F64 = 0, 1
+GPK_FULL, GPK_LOWER = 0, 1
+GPK_GEMM_LOWER_ONLY, GPK_GEMM_A_LOWER, GPK_GEMM_COLSUMSQ = 1, 2, 4
+GPK_MAX_CHILDREN = 8
+
+(K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_RQ, K_EXPONENTIAL, K_LINEAR, K_WHITE, K_CONSTANT, K_SUM,
+ K_PRODUCT) = range(11)
+
+
+class KNode(ctypes.Structure):
+    """Mirror of `gpk_knode` (include/gpk.h)."""
+
+    _fields_ = [
+        ("op", c_int32),
+        ("n_children", c_int32),
+        ("child", c_int32 * GPK_MAX_CHILDREN),
+        ("variance", c_double),
+        ("lengthscale", c_double),
+        ("alpha", c_double),
+        ("n_dims", c_int32),
+        ("dims_off", c_int32),
+        ("n_ard", c_int32),
+        ("ard_off", c_int32),
+    ]
+
+
+_KN = POINTER(KNode)
+_I32 = POINTER(c_int32)
+_F64 = POINTER(c_double)
+
+# name -> (restype, argtypes); every symbol include/gpk.h declares
+SIGNATURES = {
+    "gpk_version": (c_int, []),
+    "gpk_last_error": (c_char_p, []),
+    "gpk_kbuild": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                           c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "gpk_kdiag": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "gpk_potrf_ws": (c_size_t, [c_int64, c_int]),
+    "gpk_potrf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_potrf_batched": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_trsm_ws": (c_size_t, [c_int64, c_int]),
+    "gpk_trsm": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                         c_void_p]),
+    "gpk_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64,
+                         c_double, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "gpk_colsumsq": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_void_p, c_int, c_void_p]),
+    "gpk_reduce": (c_int, [c_int, c_void_p, c_int64, c_int64, c_double, c_int, c_void_p, c_int, c_void_p]),
+    "gpk_tril_sumsq": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_double, c_int, c_void_p, c_int,
+                               c_void_p]),
+    "gpk_axpby": (c_int, [c_int64, c_int64, c_double, c_void_p, c_int64, c_double, c_void_p, c_int64, c_int,
+                          c_void_p]),
+    "gpk_scale_cols": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "gpk_scale_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "gpk_add_diag": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int, c_void_p]),
+    "gpk_fill": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_void_p]),
+    "gpk_tril": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "gpk_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "gpk_gaussian_varexp_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double, c_int,
+                                        c_void_p, c_int, c_void_p]),
+    "gpk_launch_count": (c_int64, []),
+    "gpk_launch_count_reset": (None, []),
+    "gpk_prof_enable": (c_int, [c_int]),
+    "gpk_prof_read": (c_int, [_F64, POINTER(c_int64), c_int]),
+    "gpk_gpr_lml_ws": (c_size_t, [c_int64, c_int64, c_int]),
+    "gpk_gpr_lml": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_double,
+                            c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_sgpr_elbo_ws": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "gpk_sgpr_elbo": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                              c_void_p, c_int64, c_int64, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p]),
+    "gpk_svgp_elbo_ws": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "gpk_svgp_elbo": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                              c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
+                              c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgpk.so")
+_lib: Optional[ctypes.CDLL] = None
+
+
+class GpkError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Loads libgpk.so (building it in-tree with nvcc if it is absent and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise GpkError(
+                f"libgpk.so is missing and could not be built ({e}); gpflow_b200 has no CPU fallback"
+            ) from e
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gpk_version() != 1:
+        raise GpkError(f"libgpk.so ABI version {lib.gpk_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().gpk_last_error().decode("utf-8", "replace")
+        if status == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise GpkError(f"{what}: {msg} (status {status})")

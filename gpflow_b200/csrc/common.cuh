@@ -1,0 +1,86 @@
+// common.cuh — shared helpers for libgpk (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gpk.h"
+
+namespace gpk {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+// RAII event pair around one launch (active only while gpk_prof_enable(1))
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int cls, cudaStream_t s);
+  ~ProfScope();
+};
+enum { PROF_KBUILD = 0, PROF_GEMM = 1, PROF_LEAF = 2, PROF_SKINNY = 3, PROF_MISC = 4 };
+
+#define GPK_CHECK_ARG(cond, ...)        \
+  do {                                  \
+    if (!(cond)) {                      \
+      gpk::set_error(__VA_ARGS__);      \
+      return -1;                        \
+    }                                   \
+  } while (0)
+
+#define GPK_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      gpk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,    \
+                     __LINE__);                                                            \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define GPK_LAUNCH_OK()                                                                    \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    gpk::count_launch();                                                                   \
+    if (e__ != cudaSuccess) {                                                              \
+      gpk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, \
+                     __LINE__);                                                            \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define GPK_TRY(expr)         \
+  do {                        \
+    int r__ = (expr);         \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+inline size_t dtype_size(int dtype) { return dtype == GPK_F64 ? 8 : 4; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int NB = 128;  // Cholesky / TRSM leaf block
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Internal (typed, unchecked) entry points shared between translation units.
+template <typename T>
+int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
+           const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st);
+
+template <typename T>
+int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, cudaStream_t st);
+
+template <typename T>
+int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, int64_t ldb, const T* dinv,
+           cudaStream_t st);
+
+template <typename T>
+int trtri_diag_t(const T* L, int64_t n, int64_t ldl, T* dinv, cudaStream_t st);
+
+}  // namespace gpk

@@ -1,0 +1,437 @@
+// gemm.cu — general row-major GEMM  C = alpha*op(A)*op(B) + beta*C  for the Cholesky trailing
+// update (SYRK), the inverse-based TRSM steps, A A^T, A^T f and tril(q_sqrt)^T A.
+//   fp64: legacy tensor path  mma.sync.m8n8k4.f64 (DMMA) — tcgen05 has no f64 kind;
+//         the tcgen05 paths (int8-sliced fp64, 3xTF32 fp32) live in gemm_tc.cu.
+//   fp32: CUDA-core 128x128x8 register-tiled kernel (generic fallback for ragged shapes).
+// Replaces tf.linalg.matmul call sites: gpflow/models/sgpr.py:205,263, conditionals/util.py:144,157,
+// posteriors.py:497,535,539,728,734, and the GEMM inside tf.linalg.cholesky / triangular_solve.
+//
+// In-place contract used by potrf/trsm: a CTA reads every A/B element it needs before its first
+// store to C, and C tiles are 128x128, so C may alias A when n <= 128 (one column tile) and may
+// alias B when m <= 128 (one row tile).
+#include "common.cuh"
+
+namespace gpk {
+
+constexpr int GB = 128;  // CTA tile edge (both kernels)
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void atomic_add_t(T* p, T v) { atomicAdd(p, v); }
+
+// ------------------------------------------------------------------------------------------------
+// fp64: DMMA m8n8k4, 512 threads, 4x4 warps of 32x32, BK = 16
+// ------------------------------------------------------------------------------------------------
+constexpr int DK = 16;          // k chunk
+constexpr int DS_K = DK + 4;    // row stride of a k-minor tile  [128][20]
+constexpr int DS_M = GB + 4;    // row stride of a m-minor tile  [16][132]
+constexpr int DTILE = GB * DS_K;  // 2560 doubles >= 16*132 = 2112
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Loads this thread's share of one operand chunk into registers.
+// STORED_KMINOR: global operand is [rows][k] (k contiguous); else [k][rows] (rows contiguous).
+// tri: 0 none; 1 = stored matrix is lower triangular (zero where stored_col > stored_row).
+template <bool STORED_KMINOR>
+__device__ __forceinline__ void dload(double (&reg)[4], const double* P, int64_t ld, int64_t r0,
+                                      int64_t nrows, int64_t k0, int64_t kend, int tid, int tri) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 512;  // 0..2047
+    int rr, kk;
+    if (STORED_KMINOR) { kk = e % DK; rr = e / DK; } else { rr = e % GB; kk = e / GB; }
+    const int64_t gr = r0 + rr, gk = k0 + kk;
+    double v = 0.0;
+    if (gr < nrows && gk < kend) {
+      const int64_t srow = STORED_KMINOR ? gr : gk, scol = STORED_KMINOR ? gk : gr;
+      if (!(tri && scol > srow)) v = P[srow * ld + scol];
+    }
+    reg[i] = v;
+  }
+}
+
+template <bool STORED_KMINOR>
+__device__ __forceinline__ void dstore(const double (&reg)[4], double* __restrict__ S, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = tid + i * 512;
+    if (STORED_KMINOR) { const int kk = e % DK, rr = e / DK; S[rr * DS_K + kk] = reg[i]; }
+    else { const int rr = e % GB, kk = e / GB; S[kk * DS_M + rr] = reg[i]; }
+  }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(512, 1)
+gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                 int flags) {
+  const int64_t m0 = (int64_t)blockIdx.y * GB, n0 = (int64_t)blockIdx.x * GB;
+  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
+  extern __shared__ __align__(16) double dsm[];
+  double* sA = dsm;               // [2][DTILE]
+  double* sB = dsm + 2 * DTILE;   // [2][DTILE]
+  __shared__ double s_col[GB];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+
+  // k range; a lower-triangular stored A restricts it (rows of op(A) in this tile: m0..m0+127)
+  int64_t kb = 0, ke = k;
+  const int triA = (flags & GPK_GEMM_A_LOWER) ? 1 : 0;
+  if (triA) {
+    if (TA) kb = (m0 / DK) * DK;                // op(A)[i][kk] = S[kk][i], nonzero iff kk >= i
+    else ke = min(k, m0 + GB);                  // op(A)[i][kk] = S[i][kk], nonzero iff kk <= i
+  }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[4], rb[4];
+  const int nchunks = (int)((ke - kb + DK - 1) / DK);
+  if (nchunks > 0) {
+    dload<!TA>(ra, A, lda, m0, m, kb, ke, tid, triA);
+    dload<TB>(rb, B, ldb, n0, n, kb, ke, tid, 0);
+    dstore<!TA>(ra, sA, tid);
+    dstore<TB>(rb, sB, tid);
+  }
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) {
+      dload<!TA>(ra, A, lda, m0, m, kb + (int64_t)(c + 1) * DK, ke, tid, triA);
+      dload<TB>(rb, B, ldb, n0, n, kb + (int64_t)(c + 1) * DK, ke, tid, 0);
+    }
+    const double* cA = sA + cur * DTILE;
+    const double* cB = sB + cur * DTILE;
+#pragma unroll
+    for (int k4 = 0; k4 < DK; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        af[i] = !TA ? cA[(wm + i * 8 + g) * DS_K + k4 + t] : cA[(k4 + t) * DS_M + wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        bf[j] = TB ? cB[(wn + j * 8 + g) * DS_K + k4 + t] : cB[(k4 + t) * DS_M + wn + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    if (c + 1 < nchunks) {
+      dstore<!TA>(ra, sA + (cur ^ 1) * DTILE, tid);
+      dstore<TB>(rb, sB + (cur ^ 1) * DTILE, tid);
+    }
+    __syncthreads();
+  }
+
+  if (flags & GPK_GEMM_COLSUMSQ) {
+    if (tid < GB) s_col[tid] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t gi = m0 + wm + i * 8 + g;
+          const double v = alpha * acc[i][j][h];
+          if (gi < m) s += v * v;
+        }
+        // reduce over the 8 row-groups g (lanes with equal t)
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (g == 0) atomicAdd(&s_col[wn + j * 8 + 2 * t + h], s);
+      }
+    __syncthreads();
+    if (tid < GB && n0 + tid < n) atomicAdd(&C[n0 + tid], s_col[tid]);
+    return;
+  }
+
+  const bool vec_ok = ((uintptr_t)C % 16 == 0) && (ldc % 2 == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gi = m0 + wm + i * 8 + g;
+    if (gi >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gj = n0 + wn + j * 8 + 2 * t;
+      double* dst = C + gi * ldc + gj;
+      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (gj + 1 < n && vec_ok) {
+        if (beta != 0.0) {
+          const double2 old = *reinterpret_cast<const double2*>(dst);
+          v0 += beta * old.x; v1 += beta * old.y;
+        }
+        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      } else {
+        if (gj < n) dst[0] = beta != 0.0 ? v0 + beta * dst[0] : v0;
+        if (gj + 1 < n) dst[1] = beta != 0.0 ? v1 + beta * dst[1] : v1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic CUDA-core kernel (fp32 default; fp64 when GPK_FP64_SIMT=1): 128x128x8, 256 threads, 8x8
+// ------------------------------------------------------------------------------------------------
+constexpr int SK = 8;
+
+template <typename T, bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
+                 const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags) {
+  const int64_t m0 = (int64_t)blockIdx.y * GB, n0 = (int64_t)blockIdx.x * GB;
+  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
+  __shared__ __align__(16) T sA[2][SK][GB + 4];
+  __shared__ __align__(16) T sB[2][SK][GB + 4];
+  __shared__ T s_col[GB];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+  int64_t kb = 0, ke = k;
+  const int triA = (flags & GPK_GEMM_A_LOWER) ? 1 : 0;
+  if (triA) {
+    if (TA) kb = (m0 / SK) * SK; else ke = min(k, m0 + GB);
+  }
+  T acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = T(0);
+
+  T ra[4], rb[4];
+  auto gload = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;  // 0..1023 = 128 x 8
+      {
+        int rr, kk;
+        if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; }
+        const int64_t gr = m0 + rr, gk = k0 + kk;
+        T v = T(0);
+        if (gr < m && gk < ke) {
+          const int64_t srow = !TA ? gr : gk, scol = !TA ? gk : gr;
+          if (!(triA && scol > srow)) v = A[srow * lda + scol];
+        }
+        ra[i] = v;
+      }
+      {
+        int rr, kk;
+        if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; }
+        const int64_t gr = n0 + rr, gk = k0 + kk;
+        T v = T(0);
+        if (gr < n && gk < ke) v = TB ? B[gr * ldb + gk] : B[gk * ldb + gr];
+        rb[i] = v;
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      { int rr, kk; if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; } sA[buf][kk][rr] = ra[i]; }
+      { int rr, kk; if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; } sB[buf][kk][rr] = rb[i]; }
+    }
+  };
+
+  const int nchunks = (int)((ke - kb + SK - 1) / SK);
+  if (nchunks > 0) { gload(kb); sstore(0); }
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) gload(kb + (int64_t)(c + 1) * SK);
+#pragma unroll
+    for (int kk = 0; kk < SK; ++kk) {
+      T a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = sA[cur][kk][ty * 4 + i];
+        a[4 + i] = sA[cur][kk][64 + ty * 4 + i];
+        b[i] = sB[cur][kk][tx * 4 + i];
+        b[4 + i] = sB[cur][kk][64 + tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    if (c + 1 < nchunks) sstore(cur ^ 1);
+    __syncthreads();
+  }
+
+  if (flags & GPK_GEMM_COLSUMSQ) {
+    if (tid < GB) s_col[tid] = T(0);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      T s = T(0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t gi = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        const T v = alpha * acc[i][j];
+        if (gi < m) s += v * v;
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 16);  // the two ty rows held by one warp
+      if ((tid & 16) == 0) atomic_add_t(&s_col[j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4], s);
+    }
+    __syncthreads();
+    if (tid < GB && n0 + tid < n) atomic_add_t(&C[n0 + tid], s_col[tid]);
+    return;
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gi = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (gi >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t gj = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (gj >= n) continue;
+      T* dst = C + gi * ldc + gj;
+      const T v = alpha * acc[i][j];
+      *dst = beta != T(0) ? v + beta * *dst : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinny right-hand sides (n <= 16, B stored [k][n]):  A^T q_mu, A err, the TRSM updates of alpha / c
+// (conditionals/util.py:144, models/sgpr.py:263-264, logdensities.py:150).  Memory-bound on A.
+// ------------------------------------------------------------------------------------------------
+constexpr int SKN = 16;
+
+template <typename T, bool TA>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(int64_t m, int n, int64_t k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb, T beta,
+                   T* C, int64_t ldc) {
+  T acc[SKN];
+#pragma unroll
+  for (int j = 0; j < SKN; ++j) acc[j] = T(0);
+  if (!TA) {
+    // one warp per output row; lanes stride over k (row of A contiguous)
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const T* arow = A + i * lda;
+    for (int64_t kk = lane; kk < k; kk += 32) {
+      const T a = arow[kk];
+      const T* brow = B + kk * ldb;
+#pragma unroll
+      for (int j = 0; j < SKN; ++j)
+        if (j < n) acc[j] = fma(a, brow[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < SKN; ++j)
+      if (j < n) {
+        T s = warp_sum(acc[j]);
+        if (lane == 0) {
+          T* dst = C + i * ldc + j;
+          *dst = beta != T(0) ? alpha * s + beta * *dst : alpha * s;
+        }
+      }
+  } else {
+    // A stored [k][m]: one thread per output row, coalesced across threads
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int64_t kk = 0; kk < k; ++kk) {
+      const T a = A[kk * lda + i];
+      const T* brow = B + kk * ldb;
+#pragma unroll
+      for (int j = 0; j < SKN; ++j)
+        if (j < n) acc[j] = fma(a, brow[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < SKN; ++j)
+      if (j < n) {
+        T* dst = C + i * ldc + j;
+        *dst = beta != T(0) ? alpha * acc[j] + beta * *dst : alpha * acc[j];
+      }
+  }
+}
+
+template <typename T>
+static int launch_skinny(int ta, int64_t m, int n, int64_t k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
+                         T beta, T* C, int64_t ldc, cudaStream_t st) {
+  if (!ta)
+    gemm_skinny_kernel<T, false><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else
+    gemm_skinny_kernel<T, true><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static bool fp64_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_FP64_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+template <typename T>
+static int launch_simt(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
+                       const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st) {
+#define GO(TA_, TB_) gemm_simt_kernel<T, TA_, TB_><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+  if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
+  else if (ta && !tb) GO(true, false); else GO(true, true);
+#undef GO
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+static int launch_dmma(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                       int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags,
+                       cudaStream_t st) {
+  const size_t smem = 4 * DTILE * sizeof(double);  // 80 KB
+  static bool attr_done = false;
+  if (!attr_done) {
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+#define GO(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, 512, smem, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+  if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
+  else if (ta && !tb) GO(true, false); else GO(true, true);
+#undef GO
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T>
+int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda, const T* B,
+           int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return 0;
+  // skinny right-hand side: never when C aliases an operand row-block larger than one thread's reach
+  if (n <= SKN && !transb && flags == 0 && (const void*)C != (const void*)B && (const void*)C != (const void*)A) {
+    ProfScope ps(PROF_SKINNY, st);
+    return launch_skinny<T>(transa, m, (int)n, k, alpha, A, lda, B, ldb, beta, C, ldc, st);
+  }
+  ProfScope ps(PROF_GEMM, st);
+  dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB));
+  GPK_CHECK_ARG(grid.y <= 65535, "gemm: m too large for the grid");
+  if (sizeof(T) == 8 && !fp64_simt())
+    return launch_dmma(transa, transb, grid, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
+                       (double)beta, (double*)C, ldc, flags, st);
+  return launch_simt<T>(transa, transb, grid, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st);
+}
+
+template int gemm_t<float>(int, int, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t,
+                           float, float*, int64_t, int, cudaStream_t);
+template int gemm_t<double>(int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*,
+                            int64_t, double, double*, int64_t, int, cudaStream_t);
+
+}  // namespace gpk

@@ -1,0 +1,407 @@
+// kbuild.cu — fused pairwise covariance builder (K-build) for sm_100a.
+//
+// One pass over the output: each CTA owns a 64x64 tile of K, stages the (weighted) active columns
+// of its X / X2 row blocks in shared memory, forms the Gram term with a 4x4 register micro-tile,
+// turns it into the scaled squared distance with the norm expansion the reference uses
+// (gpflow/utilities/ops.py:105-122, on inputs scaled as in kernels/stationaries.py:77-79), applies
+// every leaf function (stationaries.py:209-313, statics.py:57-91, linears.py:60-68) and folds the
+// Sum/Product tree (kernels/base.py:281-314) in registers, adds the diagonal shift
+// (utilities/model_utils.py:33-38, covariances/kuus.py:33) and writes K once with 16-byte
+// vector stores.  The reference materialises one [N,N2] temporary per elementwise op instead.
+//
+// Algorithmic HBM bytes per launch: T*(N*N2 + (N+N2)*D)  (GPK_LOWER: T*(N(N+1)/2 + N*D)).
+#include <math.h>
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gpk {
+
+constexpr int KB_MAXG = 4;      // gram groups (distinct (active_dims, weights) sets)
+constexpr int KB_MAXL = 12;     // leaves
+constexpr int KB_MAXDIMS = 256; // total active dims over groups
+constexpr int KB_MAXOPS = 32;
+constexpr int KB_OP_ADD = 0xFE, KB_OP_MUL = 0xFF;
+constexpr int KB_TILE = 64;     // output tile edge
+constexpr int KB_KC = 32;       // dims staged per chunk
+
+struct KProg {
+  int n_groups, n_leaves, n_ops, symmetric;
+  int g_ndims[KB_MAXG], g_off[KB_MAXG], g_weighted[KB_MAXG];
+  int l_type[KB_MAXL], l_group[KB_MAXL];
+  double l_scale[KB_MAXL], l_var[KB_MAXL], l_alpha[KB_MAXL];
+  unsigned char ops[KB_MAXOPS];
+  short dims[KB_MAXDIMS];
+  double w[KB_MAXDIMS];
+};
+static_assert(sizeof(KProg) < 4000, "KProg must fit the kernel parameter space");
+
+// ---------------------------------------------------------------------------------------------
+// host: flatten the reference-shaped node list into groups / leaves / postfix ops
+// ---------------------------------------------------------------------------------------------
+static bool is_leaf_op(int op) { return op >= GPK_K_RBF && op <= GPK_K_CONSTANT; }
+static bool uses_gram(int op) { return op <= GPK_K_LINEAR; }
+
+static int emit_ops(const gpk_knode* nodes, int idx, const std::vector<int>& leaf_of, KProg& p, int& depth,
+                    int& max_depth) {
+  const gpk_knode& nd = nodes[idx];
+  if (is_leaf_op(nd.op)) {
+    if (p.n_ops >= KB_MAXOPS) return -1;
+    p.ops[p.n_ops++] = (unsigned char)leaf_of[idx];
+    depth++;
+    if (depth > max_depth) max_depth = depth;
+    return 0;
+  }
+  if (nd.n_children < 1 || nd.n_children > GPK_MAX_CHILDREN) return -1;
+  for (int c = 0; c < nd.n_children; ++c) {
+    if (nd.child[c] < 0 || nd.child[c] >= idx) return -1;  // children precede parents
+    if (emit_ops(nodes, nd.child[c], leaf_of, p, depth, max_depth)) return -1;
+    if (c > 0) {
+      if (p.n_ops >= KB_MAXOPS) return -1;
+      p.ops[p.n_ops++] = nd.op == GPK_K_SUM ? KB_OP_ADD : KB_OP_MUL;
+      depth--;
+    }
+  }
+  return 0;
+}
+
+int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, int64_t D,
+                  KProg& p) {
+  memset(&p, 0, sizeof(p));
+  GPK_CHECK_ARG(nodes && n_nodes > 0, "kbuild: empty kernel expression");
+  GPK_CHECK_ARG(D > 0 && D < 32768, "kbuild: bad input dimension D=%lld", (long long)D);
+  std::vector<int> leaf_of(n_nodes, -1);
+  int tot_dims = 0;
+  for (int i = 0; i < n_nodes; ++i) {
+    const gpk_knode& nd = nodes[i];
+    GPK_CHECK_ARG(nd.op >= GPK_K_RBF && nd.op <= GPK_K_PRODUCT, "kbuild: unknown kernel op %d", nd.op);
+    if (!is_leaf_op(nd.op)) continue;
+    GPK_CHECK_ARG(p.n_leaves < KB_MAXL, "kbuild: more than %d leaf kernels", KB_MAXL);
+    int l = p.n_leaves++;
+    leaf_of[i] = l;
+    p.l_type[l] = nd.op;
+    p.l_var[l] = nd.variance;
+    p.l_alpha[l] = nd.alpha;
+    p.l_scale[l] = 1.0;
+    p.l_group[l] = -1;
+    if (!uses_gram(nd.op)) continue;
+    int nd_dims = nd.n_dims > 0 ? nd.n_dims : (int)D;
+    GPK_CHECK_ARG(nd.n_dims == 0 || dims != nullptr, "kbuild: active dims given without index array");
+    GPK_CHECK_ARG(nd.n_ard == 0 || (nd.n_ard == nd_dims && ard != nullptr),
+                  "kbuild: size of ARD parameter (%d) does not match active dims (%d)", nd.n_ard, nd_dims);
+    // weights of this leaf's gram term
+    std::vector<double> w;
+    if (nd.n_ard > 0) {
+      w.resize(nd_dims);
+      for (int d = 0; d < nd_dims; ++d) {
+        double a = ard[nd.ard_off + d];
+        w[d] = nd.op == GPK_K_LINEAR ? a : 1.0 / (a * a);
+      }
+      if (nd.op == GPK_K_LINEAR) p.l_var[l] = 1.0;
+    } else if (nd.op != GPK_K_LINEAR) {
+      p.l_scale[l] = 1.0 / (nd.lengthscale * nd.lengthscale);
+    }
+    // find or create the group
+    int g = -1;
+    for (int c = 0; c < p.n_groups && g < 0; ++c) {
+      if (p.g_ndims[c] != nd_dims || (p.g_weighted[c] != 0) != (!w.empty())) continue;
+      bool same = true;
+      for (int d = 0; d < nd_dims && same; ++d) {
+        int col = nd.n_dims > 0 ? dims[nd.dims_off + d] : d;
+        same = p.dims[p.g_off[c] + d] == col && (w.empty() || p.w[p.g_off[c] + d] == w[d]);
+      }
+      if (same) g = c;
+    }
+    if (g < 0) {
+      GPK_CHECK_ARG(p.n_groups < KB_MAXG, "kbuild: more than %d distinct (active_dims, ARD) groups", KB_MAXG);
+      GPK_CHECK_ARG(tot_dims + nd_dims <= KB_MAXDIMS, "kbuild: more than %d active dims in total", KB_MAXDIMS);
+      g = p.n_groups++;
+      p.g_ndims[g] = nd_dims;
+      p.g_off[g] = tot_dims;
+      p.g_weighted[g] = w.empty() ? 0 : 1;
+      for (int d = 0; d < nd_dims; ++d) {
+        int col = nd.n_dims > 0 ? dims[nd.dims_off + d] : d;
+        GPK_CHECK_ARG(col >= 0 && col < D, "kbuild: active dim %d out of range [0,%lld)", col, (long long)D);
+        p.dims[tot_dims + d] = (short)col;
+        p.w[tot_dims + d] = w.empty() ? 1.0 : w[d];
+      }
+      tot_dims += nd_dims;
+    }
+    p.l_group[l] = g;
+  }
+  int depth = 0, max_depth = 0;
+  GPK_CHECK_ARG(emit_ops(nodes, n_nodes - 1, leaf_of, p, depth, max_depth) == 0,
+                "kbuild: malformed or too large kernel expression (max %d postfix ops)", KB_MAXOPS);
+  GPK_CHECK_ARG(max_depth <= 4, "kbuild: kernel expression nests deeper than the 4-entry evaluation stack");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct KMath;
+template <>
+struct KMath<double> {
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+};
+template <>
+struct KMath<float> {
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+};
+
+// value of one leaf given the (weighted) gram term `dot` and the row / column norms
+template <typename T>
+__device__ __forceinline__ T leaf_value(int type, T dot, T na, T nb, T scale, T var, T alpha, bool on_diag) {
+  using M = KMath<T>;
+  if (type == GPK_K_LINEAR) return var * dot;
+  if (type == GPK_K_CONSTANT) return var;
+  if (type == GPK_K_WHITE) return on_diag ? var : T(0);
+  T r2 = scale * (na + nb - T(2) * dot);  // ops.py:113-122 — may be slightly negative
+  if (type == GPK_K_RBF) return var * M::exp_(T(-0.5) * r2);                 // stationaries.py:210
+  if (type == GPK_K_RQ) return var * M::pow_(T(1) + T(0.5) * r2 / alpha, -alpha);  // :238
+  T r = M::sqrt_(fmax(r2, T(1e-36)));                                         // :114
+  if (type == GPK_K_MATERN52) {                                               // :311-313
+    const T s5 = T(2.23606797749978969641);
+    return var * (T(1) + s5 * r + T(5.0 / 3.0) * r * r) * M::exp_(-s5 * r);
+  }
+  if (type == GPK_K_MATERN32) {                                               // :290-292
+    const T s3 = T(1.73205080756887729353);
+    return var * (T(1) + s3 * r) * M::exp_(-s3 * r);
+  }
+  if (type == GPK_K_MATERN12) return var * M::exp_(-r);                       // :270-271
+  return var * M::exp_(T(-0.5) * r);                                          // Exponential :250-251
+}
+
+template <typename T, int NG>
+__global__ void __launch_bounds__(256)
+kbuild_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
+              const T* __restrict__ X2, int64_t N2, int64_t ldx2, T* __restrict__ K, int64_t ldk, int lower,
+              T diag_scalar, const T* __restrict__ diag_vec, int vec_ok) {
+  const int bx = blockIdx.x, by = blockIdx.y;
+  if (lower && bx > by) return;
+  __shared__ __align__(16) T sA[KB_KC][KB_TILE];
+  __shared__ __align__(16) T sB[KB_KC][KB_TILE];
+  __shared__ T sNa[NG][KB_TILE];
+  __shared__ T sNb[NG][KB_TILE];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)by * KB_TILE, col0 = (int64_t)bx * KB_TILE;
+  const bool sym = prog.symmetric != 0;
+  const T* Xb = sym ? X : X2;
+  const int64_t ldb = sym ? ldx : ldx2;
+
+  T dots[NG][4][4];
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dots[g][r][c] = T(0);
+
+  if (tid < KB_TILE) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      sNa[g][tid] = T(0);
+      sNb[g][tid] = T(0);
+    }
+  }
+
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (g >= prog.n_groups) break;
+    const int nd = prog.g_ndims[g], off = prog.g_off[g];
+    for (int d0 = 0; d0 < nd; d0 += KB_KC) {
+      const int kc = min(KB_KC, nd - d0);
+      __syncthreads();
+      // stage: sA[d][r] = w_d * X[row0+r, dims[d]],  sB[d][c] = X2[col0+c, dims[d]]
+      for (int e = tid; e < kc * KB_TILE; e += 256) {
+        const int d = e % kc, r = e / kc;  // consecutive threads walk one row's dims (same cache lines)
+        const int col = prog.dims[off + d0 + d];
+        const int64_t gr = row0 + r, gc = col0 + r;
+        T a = gr < N ? X[gr * ldx + col] : T(0);
+        T b = gc < N2 ? Xb[gc * ldb + col] : T(0);
+        sA[d][r] = a * T(prog.w[off + d0 + d]);
+        sB[d][r] = b;
+      }
+      __syncthreads();
+      // norms of this chunk (weighted): threads 0..63 rows, 64..127 columns
+      if (tid < 2 * KB_TILE) {
+        const int r = tid & (KB_TILE - 1);
+        T acc = T(0);
+        if (tid < KB_TILE) {
+          for (int d = 0; d < kc; ++d) {
+            T a = sA[d][r];
+            T wv = T(prog.w[off + d0 + d]);
+            acc += wv != T(0) ? a * a / wv : T(0);
+          }
+          sNa[g][r] += acc;
+        } else {
+          for (int d = 0; d < kc; ++d) {
+            T b = sB[d][r];
+            acc += T(prog.w[off + d0 + d]) * b * b;
+          }
+          sNb[g][r] += acc;
+        }
+      }
+      // gram micro-tile
+      for (int d = 0; d < kc; ++d) {
+        T a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = sA[d][ty * 4 + r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = sB[d][tx * 4 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dots[g][r][c] = fma(a[r], b[c], dots[g][r][c]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // epilogue: leaf functions + postfix Sum/Product fold, one output element at a time
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = row0 + ty * 4 + r;
+    T out[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t gj = col0 + tx * 4 + c;
+      const bool on_diag = sym && gi == gj;
+      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+      for (int o = 0; o < prog.n_ops; ++o) {
+        const int op = prog.ops[o];
+        if (op < KB_MAXL) {
+          const int g = prog.l_group[op];
+          T dot = T(0), na = T(0), nb = T(0);
+#pragma unroll
+          for (int gg = 0; gg < NG; ++gg)
+            if (g == gg) {
+              dot = dots[gg][r][c];
+              na = sNa[gg][ty * 4 + r];
+              nb = sNb[gg][tx * 4 + c];
+            }
+          T v = leaf_value<T>(prog.l_type[op], dot, na, nb, T(prog.l_scale[op]), T(prog.l_var[op]),
+                              T(prog.l_alpha[op]), on_diag);
+          s3 = s2; s2 = s1; s1 = s0; s0 = v;
+        } else {
+          s0 = op == KB_OP_ADD ? s1 + s0 : s1 * s0;
+          s1 = s2; s2 = s3;
+        }
+      }
+      if (on_diag) s0 += diag_scalar + (diag_vec ? diag_vec[gi] : T(0));
+      out[c] = s0;
+    }
+    if (gi < N) {
+      const int64_t gj0 = col0 + tx * 4;
+      T* dst = K + gi * ldk + gj0;
+      if (vec_ok && gj0 + 3 < N2) {
+        if (sizeof(T) == 8) {
+          reinterpret_cast<double2*>(dst)[0] = make_double2((double)out[0], (double)out[1]);
+          reinterpret_cast<double2*>(dst)[1] = make_double2((double)out[2], (double)out[3]);
+        } else {
+          reinterpret_cast<float4*>(dst)[0] = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gj0 + c < N2) dst[c] = out[c];
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void kdiag_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
+                             T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+  for (int o = 0; o < prog.n_ops; ++o) {
+    const int op = prog.ops[o];
+    if (op < KB_MAXL) {
+      T v = T(prog.l_var[op]);  // stationaries.py:82-83, statics.py:41-42
+      if (prog.l_type[op] == GPK_K_LINEAR) {  // linears.py:67-68
+        const int g = prog.l_group[op];
+        T acc = T(0);
+        for (int d = 0; d < prog.g_ndims[g]; ++d) {
+          T x = X[i * ldx + prog.dims[prog.g_off[g] + d]];
+          acc += T(prog.w[prog.g_off[g] + d]) * x * x;
+        }
+        v *= acc;
+      }
+      s3 = s2; s2 = s1; s1 = s0; s0 = v;
+    } else {
+      s0 = op == KB_OP_ADD ? s1 + s0 : s1 * s0;
+      s1 = s2; s2 = s3;
+    }
+  }
+  out[i] = s0;
+}
+
+template <typename T>
+static int kbuild_launch(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2,
+                         int64_t ldx2, void* K, int64_t ldk, int lower, double diag_scalar, const void* diag_vec,
+                         cudaStream_t st) {
+  ProfScope ps(PROF_KBUILD, st);
+  dim3 grid((unsigned)((N2 + KB_TILE - 1) / KB_TILE), (unsigned)((N + KB_TILE - 1) / KB_TILE));
+  const int vec_ok = ((uintptr_t)K % 16 == 0) && ((ldk * sizeof(T)) % 16 == 0);
+#define GPK_KB_GO(NG)                                                                                            \
+  kbuild_kernel<T, NG><<<grid, 256, 0, st>>>(p, (const T*)X, N, ldx, (const T*)X2, N2, ldx2, (T*)K, ldk, lower,   \
+                                              (T)diag_scalar, (const T*)diag_vec, vec_ok)
+  switch (p.n_groups) {
+    case 0:
+    case 1: GPK_KB_GO(1); break;
+    case 2: GPK_KB_GO(2); break;
+    case 3: GPK_KB_GO(3); break;
+    default: GPK_KB_GO(4); break;
+  }
+#undef GPK_KB_GO
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+int kbuild_impl(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* X,
+                int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2, int64_t D, void* K, int64_t ldk,
+                int dtype, int uplo, double diag_scalar, const void* diag_vec, cudaStream_t st) {
+  GPK_CHECK_ARG(dtype == GPK_F32 || dtype == GPK_F64, "kbuild: bad dtype %d", dtype);
+  GPK_CHECK_ARG(X && K, "kbuild: null X or K");
+  const bool sym = X2 == nullptr;
+  if (sym) { N2 = N; ldx2 = ldx; }
+  GPK_CHECK_ARG(N >= 0 && N2 >= 0 && ldx >= D && ldx2 >= D && ldk >= N2, "kbuild: bad shape/stride");
+  GPK_CHECK_ARG(sym || (uplo == GPK_FULL && diag_scalar == 0.0 && diag_vec == nullptr),
+                "kbuild: uplo=LOWER / diagonal shift need the symmetric form (X2 == NULL)");
+  if (N == 0 || N2 == 0) return 0;
+  KProg p;
+  GPK_TRY(compile_kprog(nodes, n_nodes, dims, ard, D, p));
+  p.symmetric = sym ? 1 : 0;
+  if (dtype == GPK_F64)
+    return kbuild_launch<double>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);
+  return kbuild_launch<float>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);
+}
+
+int kdiag_impl(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* X,
+               int64_t N, int64_t ldx, int64_t D, void* out, int dtype, cudaStream_t st) {
+  GPK_CHECK_ARG(dtype == GPK_F32 || dtype == GPK_F64, "kdiag: bad dtype %d", dtype);
+  GPK_CHECK_ARG(X && out && ldx >= D, "kdiag: bad arguments");
+  if (N == 0) return 0;
+  KProg p;
+  GPK_TRY(compile_kprog(nodes, n_nodes, dims, ard, D, p));
+  const unsigned blocks = (unsigned)((N + 255) / 256);
+  if (dtype == GPK_F64)
+    kdiag_kernel<double><<<blocks, 256, 0, st>>>(p, (const double*)X, N, ldx, (double*)out);
+  else
+    kdiag_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)X, N, ldx, (float*)out);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace gpk

@@ -1,0 +1,129 @@
+"""Sparse GP regression, Titsias bound (mirrors gpflow/models/sgpr.py:40-289, 346-377, 535-581)."""
+from __future__ import annotations
+
+from typing import Any, NamedTuple, Optional, Tuple
+
+from .. import _lib, config, covariances, ops, posteriors
+from ..inducing_variables import InducingPoints, inducingpoint_wrapper
+from ..kernels import Kernel, compile_kernel
+from ..likelihoods import Gaussian
+from ..mean_functions import MeanFunction, Zero
+from .model import GPModel, InternalDataTrainingLossMixin, data_input_to_tensor
+
+_WS_CACHE = {}
+
+
+def _sgpr_fused(X, Y, kernel, inducing_variable, likelihood, mean_function, cache=None, jitter=None):
+    """One gpk_sgpr_elbo call; returns the device fp64 vector
+    [elbo, const, logdet, quad, trace_k, trace_q, half_logdet_b, info]."""
+    lib = _lib.load()
+    N, D = X.shape
+    P = Y.shape[1]
+    Z = ops.to_device(inducing_variable.Z)
+    M = Z.shape[0]
+    dc = ops.dtype_code(X)
+    need = lib.gpk_sgpr_elbo_ws(N, M, P, dc)
+    key = (str(X.device), need)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = ops.scratch_bytes(need)
+    out = ops.torch().empty((8,), dtype=ops.torch().float64, device=X.device)
+    if mean_function is None or isinstance(mean_function, Zero):
+        Yc = Y
+    else:
+        Yc = ops.axpby(-1.0, mean_function(X), 1.0, ops.copy(Y))
+    nodes, n_nodes, dims, ard = compile_kernel(kernel, D)
+    cL, cLB, cc = cache if cache is not None else (None, None, None)
+    _lib.check(lib.gpk_sgpr_elbo(nodes, n_nodes, dims, ard, ops._p(X), N, ops._ld(X), D, ops._p(Yc), P, ops._p(Z), M,
+                                 ops._ld(Z), likelihood._variance_value(),
+                                 config.default_jitter() if jitter is None else jitter, dc, ops._p(out), ops._p(cL),
+                                 ops._p(cLB), ops._p(cc), ops._p(ws), ops._stream()), "gpk_sgpr_elbo")
+    return out
+
+
+class SGPR(GPModel, InternalDataTrainingLossMixin):
+    class CommonTensors(NamedTuple):
+        sigma_sq: Any
+        sigma: Any
+        A: Any
+        B: Any
+        LB: Any
+        AAT: Any
+        L: Any
+
+    def __init__(self, data, kernel: Kernel, inducing_variable, *, mean_function: Optional[MeanFunction] = None,
+                 num_latent_gps: Optional[int] = None, noise_variance: Any = None,
+                 likelihood: Optional[Gaussian] = None):
+        assert (noise_variance is None) or (likelihood is None), "Cannot set both `noise_variance` and `likelihood`."
+        if likelihood is None:
+            if noise_variance is None:
+                noise_variance = 1.0  # sgpr.py:71-74
+            likelihood = Gaussian(noise_variance)
+        X_data, Y_data = data_input_to_tensor(data)
+        num_latent_gps = Y_data.shape[-1] if num_latent_gps is None else num_latent_gps
+        super().__init__(kernel, likelihood, mean_function, num_latent_gps=num_latent_gps)
+        self.data = X_data, Y_data
+        self.num_data = X_data.shape[0]
+        self.inducing_variable: InducingPoints = inducingpoint_wrapper(inducing_variable)
+        self._last = None
+
+    def maximum_log_likelihood_objective(self):  # sgpr.py:170-171
+        return self.elbo()
+
+    def elbo(self):
+        """sgpr.py:276-289 in one fused call; device fp64 scalar."""
+        X, Y = self.data
+        self._last = _sgpr_fused(X, Y, self.kernel, self.inducing_variable, self.likelihood, self.mean_function)
+        return self._last[0]
+
+    def elbo_terms(self):
+        """(const, logdet_term, quad_term) of the last evaluation as device scalars (sgpr.py:214-271)."""
+        if self._last is None:
+            self.elbo()
+        return self._last[1], self._last[2], self._last[3]
+
+    def _common_calculation(self) -> "SGPR.CommonTensors":
+        """sgpr.py:181-209 built from the individual operators (kept for API parity / testing)."""
+        X, _ = self.data
+        iv = self.inducing_variable
+        s2 = self.likelihood._variance_value()
+        sigma_sq = ops.full((X.shape[0],), s2, like=X)
+        sigma = ops.full((X.shape[0],), s2 ** 0.5, like=X)
+        kuf = covariances.Kuf(iv, self.kernel, X)
+        kuu = covariances.Kuu(iv, self.kernel, jitter=config.default_jitter())
+        L, dinv = ops.cholesky(kuu)
+        A = ops.scale_cols_(kuf, sigma, invert=True)
+        ops.trsm(L, A, dinv=dinv)
+        AAT = ops.gemm(A, A, transb=True)
+        B = ops.add_diag_(ops.copy(AAT), 1.0)
+        LB, _ = ops.cholesky(B)
+        return self.CommonTensors(sigma_sq, sigma, A, B, LB, AAT, L)
+
+    def compute_qu(self) -> Tuple[Any, Any]:
+        """sgpr.py:346-377: mean [M, P] and covariance [M, M] of q(u)."""
+        X, Y = self.data
+        s2 = self.likelihood._variance_value()
+        kuf = covariances.Kuf(self.inducing_variable, self.kernel, X)
+        kuu = covariances.Kuu(self.inducing_variable, self.kernel, jitter=config.default_jitter())
+        sig = ops.copy(kuu)
+        ops.gemm(kuf, kuf, transb=True, alpha=1.0 / s2, beta=1.0, out=sig)      # kuu + kuf kuf^T / s2
+        sig_sqrt, dinv = ops.cholesky(sig)
+        sig_sqrt_kuu = ops.trsm(sig_sqrt, ops.copy(kuu), dinv=dinv)
+        cov = ops.gemm(sig_sqrt_kuu, sig_sqrt_kuu, transa=True)
+        err = Y if isinstance(self.mean_function, Zero) else ops.axpby(-1.0, self.mean_function(X), 1.0, ops.copy(Y))
+        rhs = ops.gemm(kuf, err, alpha=1.0 / s2)                                # scaled_kuf @ scaled_err
+        ops.trsm(sig_sqrt, rhs, dinv=dinv)
+        mu = ops.gemm(sig_sqrt_kuu, rhs, transa=True)
+        return mu, cov
+
+    def posterior(self, precompute_cache=posteriors.PrecomputeCacheType.TENSOR) -> posteriors.SGPRPosterior:
+        """sgpr.py:535-566."""
+        return posteriors.SGPRPosterior(kernel=self.kernel, data=self.data, inducing_variable=self.inducing_variable,
+                                        likelihood=self.likelihood, num_latent_gps=self.num_latent_gps,
+                                        mean_function=self.mean_function,
+                                        precompute_cache=posteriors._validate_precompute_cache_type(precompute_cache))
+
+    def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):  # sgpr.py:568-581
+        return self.posterior(posteriors.PrecomputeCacheType.NOCACHE).fused_predict_f(
+            Xnew, full_cov=full_cov, full_output_cov=full_output_cov)

@@ -1,0 +1,45 @@
+"""Multi-threaded CPU evaluation of the oracle's GPR log marginal likelihood, used ONLY as the timed
+CPU baseline (`bench.py` cpu_baseline / `--impl reference`).  Same arithmetic as
+oracle.gp_oracle.gpr_log_marginal_likelihood (gpflow/models/gpr.py:91-107): the covariance is built in
+row blocks on a thread pool (NumPy ufuncs release the GIL) — exactly K(X[blk], X) of the oracle kernel
+objects — and LAPACK/OpenBLAS does the Cholesky and triangular solve on all cores.  TensorFlow's CPU
+path likewise runs its elementwise ops and Eigen/LAPACK kernels on the intra-op thread pool."""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import gp_oracle as O
+
+
+def _has_white(k) -> bool:
+    if isinstance(k, O.White):
+        return True
+    return any(_has_white(c) for c in getattr(k, "kernels", []))
+
+
+def kernel_matrix_threaded(kernel, X: np.ndarray, threads: int, block: int = 256) -> np.ndarray:
+    if _has_white(kernel):  # White.K(X, X2) == 0 for explicit X2 (statics.py:61-63): no block form
+        return kernel(X)
+    N = X.shape[0]
+    K = np.empty((N, N), dtype=X.dtype)
+
+    def work(i0: int) -> None:
+        i1 = min(N, i0 + block)
+        K[i0:i1] = kernel(X[i0:i1], X)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(0, N, block)))
+    return K
+
+
+def gpr_lml_threaded(X, Y, kernel, noise_variance, threads: int | None = None) -> float:
+    threads = threads or os.cpu_count() or 1
+    K = kernel_matrix_threaded(kernel, X, threads)
+    idx = np.arange(K.shape[0])
+    K[idx, idx] += noise_variance                      # model_utils.py:33-38
+    L = O.cholesky(K)                                  # gpr.py:102
+    m = np.zeros_like(Y)
+    return float(np.sum(O.multivariate_normal(Y, m, L)))  # logdensities.py:139-156, gpr.py:107

@@ -370,9 +370,9 @@ def base_conditional_with_lm(Kmn, Lm, Knn, f, *, full_cov=False, q_sqrt=None, wh
             LTA = A[None] * q_sqrt.T[:, :, None]  # util.py:149
         else:
             Lq = np.tril(q_sqrt)  # util.py:151 band_part(-1, 0)
-            LTA = np.einsum("rkm,kn->rmn", Lq, A)  # util.py:157  (L^T A per r)
+            LTA = np.matmul(np.transpose(Lq, (0, 2, 1)), A)  # util.py:157  (L^T A per r)
         if full_cov:
-            fvar = fvar + np.einsum("rmn,rmk->rnk", LTA, LTA)
+            fvar = fvar + np.matmul(np.transpose(LTA, (0, 2, 1)), LTA)
         else:
             fvar = fvar + np.sum(np.square(LTA), -2)  # util.py:164
     if not full_cov:

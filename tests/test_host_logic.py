@@ -1,0 +1,172 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, host-side descriptor
+compilation, dispatch, parameters, config, argument errors (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpflow_b200 as gpf
+from gpflow_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "gpk.h")).read()
+    declared = set(re.findall(r"GPK_API\s+[\w\s\*]+?\b(gpk_\w+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gpk_version() == 1
+
+
+def test_knode_struct_matches_header_layout():
+    # int32 op, n_children, child[8]; 3 doubles; 4 int32
+    assert ctypes.sizeof(_lib.KNode) == 4 * 10 + 8 * 3 + 4 * 4
+    assert _lib.KNode.variance.offset == 40 and _lib.KNode.n_dims.offset == 64
+
+
+def test_compile_kernel_tree_and_flattening():
+    k = gpf.kernels
+    expr = (k.RBF(lengthscales=2.0) + k.Matern32(lengthscales=4.0)) * k.Linear()
+    nodes, n, dims, ard = k.compile_kernel(expr, 5)
+    assert n == 5
+    assert [nd.op for nd in nodes] == [_lib.K_RBF, _lib.K_MATERN32, _lib.K_SUM, _lib.K_LINEAR, _lib.K_PRODUCT]
+    assert list(nodes[2].child)[:2] == [0, 1] and list(nodes[4].child)[:2] == [2, 3]
+    # same-class nesting is flattened (gpflow/kernels/base.py:246-254)
+    s = (k.RBF() + k.Matern12()) + k.White()
+    assert len(s.kernels) == 3
+    p = (k.RBF() * k.Matern12()) * k.White()
+    assert len(p.kernels) == 3
+    assert len(((k.RBF() + k.Matern12()) * k.White()).kernels) == 2
+
+
+def test_compile_kernel_active_dims_and_ard():
+    k = gpf.kernels
+    kern = k.RBF(lengthscales=[1.0, 2.0], active_dims=[0, 3]) + k.Linear(variance=[0.5, 0.25, 2.0], active_dims=slice(1, 4))
+    nodes, n, dims, ard = k.compile_kernel(kern, 5)
+    assert nodes[0].n_dims == 2 and list(dims)[:2] == [0, 3] and nodes[0].n_ard == 2
+    assert nodes[1].n_dims == 3 and list(dims)[2:5] == [1, 2, 3] and list(ard)[2:5] == [0.5, 0.25, 2.0]
+    with pytest.raises(ValueError):  # gpflow/kernels/base.py:164-168
+        k.RBF(lengthscales=[1.0, 2.0, 3.0], active_dims=[0, 1])
+    with pytest.raises(ValueError):
+        k.compile_kernel(k.RBF(active_dims=[7]), 5)
+    with pytest.raises(ValueError):
+        k.compile_kernel(k.RBF(lengthscales=[1.0, 2.0]), 5)
+    with pytest.raises(TypeError):  # stationaries.py:56-58
+        k.RBF(foo=1)
+
+
+def test_call_rejects_ambiguous_inputs():
+    with pytest.raises(ValueError):  # gpflow/kernels/base.py:203-204
+        gpf.kernels.RBF()(np.zeros((3, 2)), np.zeros((3, 2)), full_cov=False)
+
+
+def test_kbuild_argument_errors_reported_through_status():
+    lib = _lib.load()
+    nodes = (_lib.KNode * 1)()
+    nodes[0].op = 99
+    st = lib.gpk_kbuild(nodes, 1, None, None, ctypes.c_void_p(16), 4, 2, None, 4, 2, 2, ctypes.c_void_p(16), 4,
+                        _lib.GPK_F64, _lib.GPK_FULL, 0.0, None, None)
+    assert st == -1 and b"unknown kernel op" in lib.gpk_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(st, "gpk_kbuild")
+    st = lib.gpk_potrf(None, 4, 4, 4, _lib.GPK_F64, None, None, None)
+    assert st == -1
+    st = lib.gpk_gemm(0, 0, 4, 4, 4, 1.0, ctypes.c_void_p(16), 4, ctypes.c_void_p(16), 4, 0.0, ctypes.c_void_p(16), 4,
+                      7, 0, None)
+    assert st == -1 and b"dtype" in lib.gpk_last_error()
+
+
+def test_workspace_queries():
+    lib = _lib.load()
+    assert lib.gpk_potrf_ws(128, _lib.GPK_F64) == 128 * 128 * 8
+    assert lib.gpk_potrf_ws(129, _lib.GPK_F32) == 2 * 128 * 128 * 4
+    n, p = 8192, 1
+    assert lib.gpk_gpr_lml_ws(n, p, _lib.GPK_F64) >= (n + p) * n * 8
+    assert lib.gpk_sgpr_elbo_ws(1000, 100, 2, _lib.GPK_F32) > 1000 * 100 * 4
+    assert lib.gpk_svgp_elbo_ws(64, 32, 2, _lib.GPK_F32) > 0
+
+
+def test_dispatcher_plugin_mechanism():
+    from gpflow_b200.utilities import Dispatcher
+
+    d = Dispatcher("demo")
+
+    class A: ...
+    class B(A): ...
+
+    @d.register(A, object)
+    def _a(x, y):
+        return "A"
+
+    @d.register(B, int)
+    def _b(x, y):
+        return "B"
+
+    assert d(A(), 1) == "A" and d(B(), 1) == "B" and d(B(), "s") == "A"
+    with pytest.raises(NotImplementedError):
+        d(1, 2)
+    assert d.dispatch_or_raise(B, int) is _b
+    # the reference registries exist with the same names
+    from gpflow_b200 import covariances, kullback_leiblers, posteriors
+    assert covariances.Kuu.dispatch(gpf.inducing_variables.InducingPoints, gpf.kernels.RBF) is not None
+    assert covariances.Kuf.dispatch(gpf.inducing_variables.InducingPoints, gpf.kernels.RBF, np.ndarray) is not None
+    assert posteriors.get_posterior_class(gpf.kernels.RBF(), gpf.inducing_variables.InducingPoints(np.zeros((2, 1)))) \
+        is posteriors.IndependentPosteriorSingleOutput
+
+
+def test_parameter_transforms_and_bounds():
+    from gpflow_b200.base import Parameter, positive
+
+    p = Parameter(0.3, transform=positive())
+    assert np.isclose(np.logaddexp(0, p.unconstrained_variable), 0.3)
+    with pytest.raises(ValueError):
+        Parameter(-1.0, transform=positive())
+    lik = gpf.likelihoods.Gaussian(0.1)
+    with pytest.raises(ValueError):  # lower bound 1e-6, scalar_continuous.py:70-77
+        lik.variance.assign(1e-7)
+    m = gpf.kernels.RBF() + gpf.kernels.White()
+    assert len(m.parameters) == 3 and len(m.trainable_parameters) == 3
+    gpf.set_trainable(m.kernels[1], False)
+    assert len(m.trainable_parameters) == 2
+
+
+def test_config_defaults_and_context():
+    c = gpf.config
+    assert c.default_float() is np.float64 and c.default_jitter() == 1e-6
+    with c.as_context(c.Config(float=np.float32, jitter=1e-4)):
+        assert c.default_float() is np.float32 and c.default_jitter() == 1e-4
+        assert gpf.Parameter(1.0).dtype == np.float32
+    assert c.default_float() is np.float64
+    with pytest.raises(TypeError):
+        c.set_default_float(np.int32)
+
+
+def test_model_constructors_defaults_without_gpu():
+    # SVGP holds only host parameters until evaluated (gpflow/models/svgp.py:124-140)
+    m = gpf.models.SVGP(gpf.kernels.RBF(), gpf.likelihoods.Gaussian(), np.zeros((7, 2)), num_latent_gps=3)
+    assert m.q_mu.shape == (7, 3) and m.q_sqrt.shape == (3, 7, 7) and m.whiten
+    assert np.array_equal(m.q_sqrt.numpy()[1], np.eye(7))
+    m = gpf.models.SVGP(gpf.kernels.RBF(), gpf.likelihoods.Gaussian(), np.zeros((7, 2)), q_diag=True, num_latent_gps=2)
+    assert m.q_sqrt.shape == (7, 2)
+
+
+def test_product_has_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.GpkError):
+        gpf.kernels.RBF()(np.zeros((3, 2)))
+    src = ""
+    for root, _, files in os.walk(os.path.join(ROOT, "gpflow_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src += open(os.path.join(root, f)).read()
+    assert "oracle" not in src.replace("gp_oracle", "oracle") or "import oracle" not in src
+    assert "from oracle" not in src and "import oracle" not in src
