@@ -68,6 +68,7 @@ SIGNATURES = {
                                         c_void_p, c_int, c_void_p]),
     "gpk_launch_count": (c_int64, []),
     "gpk_launch_count_reset": (None, []),
+    "gpk_debug_leaf": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gpk_prof_enable": (c_int, [c_int]),
     "gpk_prof_read": (c_int, [_F64, POINTER(c_int64), c_int]),
     "gpk_gpr_lml_ws": (c_size_t, [c_int64, c_int64, c_int]),

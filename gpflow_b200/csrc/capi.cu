@@ -63,6 +63,7 @@ int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype,
   return trtri_diag_t<float>((const float*)L, n, ldl, (float*)dinv, st);
 }
 
+int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st);
 size_t gpr_lml_ws(int64_t N, int64_t P, int dtype);
 int gpr_lml(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t, const void*,
             int64_t, double, const void*, int, double*, void*, cudaStream_t);
@@ -87,6 +88,10 @@ int gpk_version(void) { return GPK_VERSION; }
 
 int64_t gpk_launch_count(void) { return (int64_t)g_launches.load(); }
 void gpk_launch_count_reset(void) { g_launches.store(0); }
+
+int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* stream) {
+  return leaf_debug((double*)A, lda, n, (double*)dinv, (long long*)dbg, (cudaStream_t)stream);
+}
 
 int gpk_prof_enable(int on) {
   for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -179,6 +179,16 @@ __device__ __forceinline__ T leaf_value(int type, T dot, T na, T nb, T scale, T 
   return var * M::exp_(T(-0.5) * r);                                          // Exponential :250-251
 }
 
+// element e (= r*4+c) of a register-resident 4x4 tile without dynamic register indexing
+template <typename T>
+__device__ __forceinline__ T sel16(const T (&d)[4][4], int e) {
+  T v = d[0][0];
+#pragma unroll
+  for (int q = 1; q < 16; ++q)
+    if (e == q) v = d[q >> 2][q & 3];
+  return v;
+}
+
 template <typename T, int NG>
 __global__ void __launch_bounds__(256)
 kbuild_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
@@ -267,53 +277,67 @@ kbuild_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64
   }
   __syncthreads();
 
-  // epilogue: leaf functions + postfix Sum/Product fold, one output element at a time
+  // epilogue: leaf functions + postfix Sum/Product fold.  The 16 elements of the micro-tile are
+  // processed by ONE rolled loop (values staged in a small local array): unrolling it replicates
+  // the exp/sqrt/pow code 16x (180 KB of SASS) and makes the kernel instruction-fetch bound.
+  T vals[16];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t gi = row0 + ty * 4 + r;
-    T out[4];
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int64_t gj = col0 + tx * 4 + c;
-      const bool on_diag = sym && gi == gj;
-      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
-      for (int o = 0; o < prog.n_ops; ++o) {
-        const int op = prog.ops[o];
-        if (op < KB_MAXL) {
-          const int g = prog.l_group[op];
-          T dot = T(0), na = T(0), nb = T(0);
+    for (int c = 0; c < 4; ++c) vals[r * 4 + c] = NG == 1 ? dots[0][r][c] : T(0);
+  const int n_ops = prog.n_ops;
+#pragma unroll 1
+  for (int e = 0; e < 16; ++e) {
+    const int r = e >> 2, c = e & 3;
+    const int64_t gi = row0 + ty * 4 + r, gj = col0 + tx * 4 + c;
+    const bool on_diag = sym && gi == gj;
+    T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+    for (int o = 0; o < n_ops; ++o) {
+      const int op = prog.ops[o];
+      if (op < KB_MAXL) {
+        const int g = prog.l_group[op];
+        T dot = T(0), na = T(0), nb = T(0);
+        if (NG == 1) {
+          dot = vals[e];
+          if (g == 0) { na = sNa[0][ty * 4 + r]; nb = sNb[0][tx * 4 + c]; }
+        } else {
 #pragma unroll
           for (int gg = 0; gg < NG; ++gg)
             if (g == gg) {
-              dot = dots[gg][r][c];
+              dot = sel16(dots[gg], e);
               na = sNa[gg][ty * 4 + r];
               nb = sNb[gg][tx * 4 + c];
             }
-          T v = leaf_value<T>(prog.l_type[op], dot, na, nb, T(prog.l_scale[op]), T(prog.l_var[op]),
-                              T(prog.l_alpha[op]), on_diag);
-          s3 = s2; s2 = s1; s1 = s0; s0 = v;
-        } else {
-          s0 = op == KB_OP_ADD ? s1 + s0 : s1 * s0;
-          s1 = s2; s2 = s3;
         }
+        T v = leaf_value<T>(prog.l_type[op], dot, na, nb, T(prog.l_scale[op]), T(prog.l_var[op]),
+                            T(prog.l_alpha[op]), on_diag);
+        s3 = s2; s2 = s1; s1 = s0; s0 = v;
+      } else {
+        s0 = op == KB_OP_ADD ? s1 + s0 : s1 * s0;
+        s1 = s2; s2 = s3;
       }
-      if (on_diag) s0 += diag_scalar + (diag_vec ? diag_vec[gi] : T(0));
-      out[c] = s0;
     }
+    if (on_diag) s0 += diag_scalar + (diag_vec ? diag_vec[gi] : T(0));
+    vals[e] = s0;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = row0 + ty * 4 + r;
     if (gi < N) {
       const int64_t gj0 = col0 + tx * 4;
       T* dst = K + gi * ldk + gj0;
       if (vec_ok && gj0 + 3 < N2) {
         if (sizeof(T) == 8) {
-          reinterpret_cast<double2*>(dst)[0] = make_double2((double)out[0], (double)out[1]);
-          reinterpret_cast<double2*>(dst)[1] = make_double2((double)out[2], (double)out[3]);
+          reinterpret_cast<double2*>(dst)[0] = make_double2((double)vals[r * 4 + 0], (double)vals[r * 4 + 1]);
+          reinterpret_cast<double2*>(dst)[1] = make_double2((double)vals[r * 4 + 2], (double)vals[r * 4 + 3]);
         } else {
-          reinterpret_cast<float4*>(dst)[0] = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
+          reinterpret_cast<float4*>(dst)[0] =
+              make_float4((float)vals[r * 4 + 0], (float)vals[r * 4 + 1], (float)vals[r * 4 + 2], (float)vals[r * 4 + 3]);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (gj0 + c < N2) dst[c] = out[c];
+          if (gj0 + c < N2) dst[c] = vals[r * 4 + c];
       }
     }
   }

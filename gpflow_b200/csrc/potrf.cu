@@ -22,14 +22,31 @@ template <typename T> __device__ __forceinline__ T sqrt_t(T x);
 template <> __device__ __forceinline__ double sqrt_t<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float sqrt_t<float>(float x) { return sqrtf(x); }
 
-// ---- 32x32 diagonal block Cholesky by one warp: lane i owns row i in registers -------------------
+// Leaf design notes (measured with gpk_debug_leaf on B200, cycles @1.9 GHz):
+//  * shared-memory read-modify-write loops serialise on load/store aliasing (~55 cycles per fma);
+//    all O(n^3) phases therefore accumulate 4x4 micro-tiles in registers from read-only operands;
+//  * micro-tiles are INTERLEAVED (thread (tr,tc) owns rows tr+TR*i, cols tc+TC*j) so the lanes of a
+//    warp touch consecutive rows of the stride-129 array: bank-conflict free;
+//  * the serial part (32x32 diagonal Cholesky, one warp) keeps its row in registers and exchanges
+//    columns by shuffles.
+
+template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
+template <> __device__ __forceinline__ double rsqrt_t<double>(double x) { return rsqrt(x); }
+template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rsqrtf(x); }
+
+// ---- 32x32 diagonal block Cholesky by one warp: lane i owns row i in registers ---------------------
+// On return S holds L (strict lower part), ldiag the diagonal of L, and S's diagonal 1/L_kk.
+// Cross-lane traffic is shuffles only (measured: 11.5k cycles; a shared-memory column broadcast
+// variant took 18.4k, a pure shared-memory loop 27k).  Chain per column: shfl -> rsqrt -> mul ->
+// shfl -> fma.
 template <typename T>
-__device__ __forceinline__ int warp_chol32(T* S, int jb, T* dinvdiag) {
+__device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   const int lane = threadIdx.x & 31;
   T a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = c <= lane ? S[(jb + lane) * LS + jb + c] : T(0);
   int bad = 0;
+  T my_inv = T(1), my_diag = T(1);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     T d = __shfl_sync(0xffffffffu, a[k], k);
@@ -37,211 +54,238 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* dinvdiag) {
       if (bad == 0) bad = k + 1;
       d = T(1);
     }
-    const T piv = sqrt_t<T>(d);
-    const T inv = T(1) / piv;
-    a[k] = lane == k ? piv : a[k] * inv;  // l_ik for lane i >= k (rows above hold zeros)
-    if (lane == k) dinvdiag[jb + k] = inv;
+    const T inv = rsqrt_t<T>(d);
+    if (lane == k) { my_inv = inv; my_diag = d * inv; }
+    a[k] *= inv;  // l_ik for lane i > k; rows above hold zeros
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 32; ++j)
       if (j > k) {
         const T ljk = __shfl_sync(0xffffffffu, a[k], j);
         if (lane >= j) a[j] -= a[k] * ljk;
       }
-    }
   }
 #pragma unroll
   for (int c = 0; c < 32; ++c)
-    if (c <= lane) S[(jb + lane) * LS + jb + c] = a[c];
+    if (c < lane) S[(jb + lane) * LS + jb + c] = a[c];
+  S[(jb + lane) * LS + jb + lane] = my_inv;  // diagonal slot now holds inv(L)_kk
+  ldiag[jb + lane] = my_diag;
+  __syncwarp();
   return bad;
 }
 
-// ---- inverse of the 128x128 lower factor held in S (lower incl. diagonal) ---------------------------
-// Result: strict lower part of Linv stored TRANSPOSED in the strict upper triangle of S
-// (Linv[r][c] = S[c][r], r > c); diagonal of Linv in dinvdiag.  tmp: 3 * 32*32 scratch.
+// ---- inverse of one 32x32 lower-triangular diagonal block by one warp ----------------------------
+// lane j solves L x = e_j with x in registers (L broadcast from shared memory); x_i (i > j) goes to
+// the TRANSPOSED slot S[jb+j][jb+i]; the diagonal slot already holds 1/L_jj.
 template <typename T>
-__device__ void invert_lower_128(T* S, T* dinvdiag, T* tmp) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // (a) diagonal 32x32 blocks: warp J, lane j solves L_JJ x = e_j
-  if (warp < 4) {
-    const int jb = warp * 32;
-    T x[32];
+__device__ __forceinline__ void warp_inv32(T* S, int jb) {
+  const int lane = threadIdx.x & 31;
+  T x[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = i == lane ? T(1) : T(0);
+  for (int i = 0; i < 32; ++i) x[i] = i == lane ? T(1) : T(0);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      x[k] *= dinvdiag[jb + k];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i > k) x[i] -= S[(jb + i) * LS + jb + k] * x[k];
-    }
-    __syncwarp();
+  for (int k = 0; k < 32; ++k) {
+    x[k] *= S[(jb + k) * LS + jb + k];
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (i > lane) S[(jb + lane) * LS + jb + i] = x[i];  // Linv[jb+i][jb+lane] -> transposed slot
+      if (i > k) x[i] -= S[(jb + i) * LS + jb + k] * x[k];
   }
-  __syncthreads();
-  auto linv = [&](int r, int c) -> T {  // r >= c
-    return r == c ? dinvdiag[r] : S[c * LS + r];
-  };
-  // (b) off-diagonal blocks by block distance d:  Linv_IJ = -Linv_II * sum_{K=J}^{I-1} L_IK Linv_KJ
+  __syncwarp();  // every lane has finished reading the lower triangle before the upper slots are written
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i > lane) S[(jb + lane) * LS + jb + i] = x[i];
+  __syncwarp();
+}
+
+// 4x4 register micro-tile accumulation: acc[i][j] += sum_k fa(i,k) * fb(j,k), k in [k0,k1)
+template <typename T, class FA, class FB>
+__device__ __forceinline__ void mt_acc(T (&acc)[4][4], int k0, int k1, FA fa, FB fb) {
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    T av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) av[i] = fa(i, k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = fb(j, k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void mt_zero(T (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+}
+
+// ---- off-diagonal 32x32 blocks of the inverse (diagonal blocks already inverted) --------------------
+// Linv is stored TRANSPOSED in the upper triangle of S INCLUDING the diagonal: Linv[r][c] = S[c][r],
+// r >= c.  The strict lower triangle of S still holds L.  tmp: 3 * 32*32 scratch.
+template <typename T>
+__device__ void invert_offdiag_128(T* S, T* tmp) {
+  const int tid = threadIdx.x;
+  const int pair = tid >> 6, sub = tid & 63;  // 64 threads (8x8, interleaved 4x4 micro-tiles) per block
+  const int tr = sub >> 3, tc = sub & 7;
+  // by block distance d:  Linv_IJ = -Linv_II * sum_{K=J}^{I-1} L_IK Linv_KJ
   for (int d = 1; d < 4; ++d) {
     const int npairs = 4 - d;
-    const int pair = tid >> 6, sub = tid & 63;       // 64 threads per 32x32 block, 4x4 micro-tiles
-    const int r0 = (sub >> 3) * 4, c0 = (sub & 7) * 4;
     const int J = pair, I = pair + d;
     T acc[4][4];
     if (pair < npairs) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+      mt_zero(acc);
       for (int K = J; K < I; ++K) {
-        // L_IK [32x32] times Linv_KJ [32x32] (lower-triangular when K == J)
-        for (int k = 0; k < 32; ++k) {
-          T av[4], bv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = S[(I * 32 + r0 + i) * LS + K * 32 + k];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int rr = K * 32 + k, cc = J * 32 + c0 + j;
-            bv[j] = rr >= cc ? linv(rr, cc) : T(0);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-        }
+        const T* La = S + (I * 32 + tr) * LS + K * 32;           // L_IK rows tr + 8 i
+        const T* Lb = S + (J * 32 + tc) * LS + K * 32;           // Linv_KJ[k][c] = S[J*32+c][K*32+k]
+        const bool tri = K == J;
+        mt_acc<T>(acc, 0, 32,
+                  [&](int i, int k) { return La[i * 8 * LS + k]; },
+                  [&](int j, int k) { const T v = Lb[j * 8 * LS + k]; return (!tri || k >= tc + 8 * j) ? v : T(0); });
       }
       T* tp = tmp + pair * 1024;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tp[(r0 + i) * 32 + c0 + j] = acc[i][j];
+        for (int j = 0; j < 4; ++j) tp[(tr + 8 * i) * 32 + tc + 8 * j] = acc[i][j];
     }
     __syncthreads();
     if (pair < npairs) {
       const T* tp = tmp + pair * 1024;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-      for (int k = 0; k < 32; ++k) {
-        T av[4], bv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = I * 32 + r0 + i, cc = I * 32 + k;
-          av[i] = rr >= cc ? linv(rr, cc) : T(0);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = tp[k * 32 + c0 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-      }
+      const T* Li = S + (I * 32) * LS + I * 32 + tr;             // Linv_II[r][k] = S[I*32+k][I*32+r], r >= k
+      mt_zero(acc);
+      mt_acc<T>(acc, 0, 32,
+                [&](int i, int k) { const T v = Li[k * LS + 8 * i]; return (tr + 8 * i >= k) ? v : T(0); },
+                [&](int j, int k) { return tp[k * 32 + tc + 8 * j]; });
       // Linv[I*32+r][J*32+c] = -acc  ->  S[J*32+c][I*32+r]
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) S[(J * 32 + c0 + j) * LS + I * 32 + r0 + i] = -acc[i][j];
+        for (int j = 0; j < 4; ++j) S[(J * 32 + tc + 8 * j) * LS + I * 32 + tr + 8 * i] = -acc[i][j];
     }
     __syncthreads();
   }
 }
 
+// coalesced, 16-deep unrolled load of the lower triangle of an n x n block (identity-padded to 128)
 template <typename T>
-__device__ __forceinline__ void write_dinv(const T* S, const T* dinvdiag, T* __restrict__ dinv) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    dinv[e] = r > c ? S[c * LS + r] : (r == c ? dinvdiag[r] : T(0));
+__device__ __forceinline__ void load_lower_block(T* S, const T* __restrict__ A, int64_t lda, int n) {
+  const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;  // 2 rows per pass
+#pragma unroll 1
+  for (int r0 = 0; r0 < NB; r0 += 32) {
+    T v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = r0 + 2 * u + rh;
+      v[u] = (r < n && c <= r) ? A[(int64_t)r * lda + c] : ((r >= n && c == r) ? T(1) : T(0));
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) S[(r0 + 2 * u + rh) * LS + c] = v[u];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void write_dinv(const T* S, T* __restrict__ dinv) {
+  const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;
+#pragma unroll 8
+  for (int r0 = 0; r0 < NB; r0 += 2) {
+    const int r = r0 + rh;
+    dinv[r * NB + c] = c <= r ? S[c * LS + r] : T(0);
   }
 }
 
 // ---- leaf: factor + invert one diagonal block (n <= 128) ------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256, 1)
-potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base) {
+potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base,
+                  long long* dbg) {
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   T* S = reinterpret_cast<T*>(leaf_smem);  // [128][129]
-  T* dinvdiag = S + NB * LS;               // [128]
-  T* tmp = dinvdiag + NB;                  // [3][32*32]
+  T* ldiag = S + NB * LS;                  // [128] diagonal of L
+  T* tmp = ldiag + NB;                     // [3][32*32] scratch (panel staging / inverse products)
   const int tid = threadIdx.x;
+  const int tr = tid >> 3, tc = tid & 7;   // 32 x 8 thread grid, interleaved 4x4 micro-tiles
 
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    T v = T(0);
-    if (r < n && c <= r) v = A[(int64_t)r * lda + c];
-    else if (r >= n && c == r) v = T(1);
-    S[r * LS + c] = v;
-  }
+#define GPK_DBG(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+  GPK_DBG(0);
+  load_lower_block<T>(S, A, lda, n);
   __syncthreads();
+  GPK_DBG(1);
 
+#pragma unroll 1
   for (int J = 0; J < 4; ++J) {
     const int jb = J * 32;
     if (tid < 32) {
-      const int bad = warp_chol32<T>(S, jb, dinvdiag);
+      const int bad = warp_chol32<T>(S, jb, ldiag);
       if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + jb + bad);
+      if (J == 0) GPK_DBG(2);
+      warp_inv32<T>(S, jb);
+      if (J == 0) GPK_DBG(3);
     }
     __syncthreads();
     const int t0 = jb + 32, nr = NB - t0;
     if (nr > 0) {
-      // panel: rows t0..127 solve x L_JJ^T = b  (one thread per row, x in registers)
-      if (tid < nr) {
-        const int r = t0 + tid;
-        T x[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = S[r * LS + jb + c];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          x[k] *= dinvdiag[jb + k];
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c > k) x[c] -= x[k] * S[(jb + c) * LS + jb + k];
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) S[r * LS + jb + c] = x[c];
-      }
-      __syncthreads();
-      // trailing update of the remaining lower blocks with 4x4 register micro-tiles
-      const int nt = nr / 4;
-      for (int e = tid; e < nt * nt; e += 256) {
-        const int ti = e / nt, tj = e % nt;
-        if (tj > ti) continue;
-        const int r0 = t0 + ti * 4, c0 = t0 + tj * 4;
-        T acc[4][4];
+      // panel rows t0..127:  X = B inv(L_JJ)^T ; inv(L_JJ)[c][k] = S[jb+k][jb+c] for k <= c
+      T acc[4][4];
+      const int ni = nr / 32;  // row groups of 32 owned by this thread grid
+      {
+        mt_zero(acc);
+        const T* Bp = S + (t0 + tr) * LS + jb;
+        const T* Ip = S + jb * LS + jb + tc;
+        mt_acc<T>(acc, 0, 32,
+                  [&](int i, int k) { return i < ni ? Bp[i * 32 * LS + k] : T(0); },
+                  [&](int j, int k) { const T v = Ip[k * LS + 8 * j]; return k <= tc + 8 * j ? v : T(0); });
 #pragma unroll
         for (int i = 0; i < 4; ++i)
+          if (i < ni)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-        for (int k = 0; k < 32; ++k) {
-          T av[4], bv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = S[(r0 + i) * LS + jb + k];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bv[j] = S[(c0 + j) * LS + jb + k];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (c0 + j <= r0 + i) S[(r0 + i) * LS + c0 + j] -= acc[i][j];
+            for (int j = 0; j < 4; ++j) tmp[(tr + 32 * i) * 32 + tc + 8 * j] = acc[i][j];
       }
       __syncthreads();
+      for (int e = tid; e < nr * 32; e += 256) S[(t0 + (e >> 5)) * LS + jb + (e & 31)] = tmp[e];
+      __syncthreads();
+      if (J == 0) GPK_DBG(4);
+      // trailing update, column blocks of 32: C[r][c] -= sum_k S[r][jb+k] S[c][jb+k], c <= r
+      for (int cb = t0; cb < NB; cb += 32) {
+        const int nib = (NB - cb) / 32;
+        mt_zero(acc);
+        const T* Ra = S + (cb + tr) * LS + jb;
+        const T* Rb = S + (cb + tc) * LS + jb;
+        mt_acc<T>(acc, 0, 32,
+                  [&](int i, int k) { return i < nib ? Ra[i * 32 * LS + k] : T(0); },
+                  [&](int j, int k) { return Rb[j * 8 * LS + k]; });
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nib)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = cb + tr + 32 * i, c = cb + tc + 8 * j;
+              if (c <= r) S[r * LS + c] -= acc[i][j];
+            }
+      }
+      __syncthreads();
+      if (J == 0) GPK_DBG(5);
     }
   }
+  GPK_DBG(6);
 
-  // L back to global (lower part of the first n rows)
-  for (int e = tid; e < n * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    if (c <= r) A[(int64_t)r * lda + c] = S[r * LS + c];
+  // L back to global (lower part of the first n rows), coalesced along columns
+  {
+    const int c = tid & 127, rh = tid >> 7;
+#pragma unroll 8
+    for (int r0 = 0; r0 < NB; r0 += 2) {
+      const int r = r0 + rh;
+      if (r < n && c <= r) A[(int64_t)r * lda + c] = c == r ? ldiag[r] : S[r * LS + c];
+    }
   }
+  GPK_DBG(7);
+  invert_offdiag_128<T>(S, tmp);
+  GPK_DBG(8);
+  write_dinv<T>(S, dinv);
   __syncthreads();
-  invert_lower_128<T>(S, dinvdiag, tmp);
-  write_dinv<T>(S, dinvdiag, dinv);
+  GPK_DBG(9);
+#undef GPK_DBG
 }
 
 // ---- standalone inverse of the diagonal blocks of a given factor (for trsm without cached dinv) -----
@@ -250,23 +294,18 @@ __global__ void __launch_bounds__(256, 1)
 trtri_diag_kernel(const T* __restrict__ L, int64_t ldl, int64_t n, T* __restrict__ dinv) {
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   T* S = reinterpret_cast<T*>(leaf_smem);
-  T* dinvdiag = S + NB * LS;
-  T* tmp = dinvdiag + NB;
+  T* tmp = S + NB * LS + NB;
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * NB;
   const int nb = (int)min((int64_t)NB, n - b0);
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    T v = T(0);
-    if (r < nb && c <= r) v = L[(b0 + r) * ldl + b0 + c];
-    else if (r >= nb && c == r) v = T(1);
-    S[r * LS + c] = v;
-  }
+  load_lower_block<T>(S, L + b0 * ldl + b0, ldl, nb);
   __syncthreads();
-  if (tid < NB) dinvdiag[tid] = T(1) / S[tid * LS + tid];
+  if (tid < NB) S[tid * LS + tid] = T(1) / S[tid * LS + tid];  // diagonal slot holds inv(L)_kk
   __syncthreads();
-  invert_lower_128<T>(S, dinvdiag, tmp);
-  write_dinv<T>(S, dinvdiag, dinv + (size_t)blockIdx.x * NB * NB);
+  if (tid < 128) warp_inv32<T>(S, (tid >> 5) * 32);
+  __syncthreads();
+  invert_offdiag_128<T>(S, tmp);
+  write_dinv<T>(S, dinv + (size_t)blockIdx.x * NB * NB);
 }
 
 template <typename T>
@@ -294,7 +333,7 @@ static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, 
     T* dblk = dinv + (size_t)(col0 / NB) * NB * NB;
     {
       ProfScope ps(PROF_LEAF, st);
-      potrf_leaf_kernel<T><<<1, 256, leaf_smem_bytes<T>(), st>>>(A, lda, (int)n, dblk, info, (int)col0);
+      potrf_leaf_kernel<T><<<1, 256, leaf_smem_bytes<T>(), st>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr);
       GPK_LAUNCH_OK();
     }
     if (rows > n)  // rows below: X = B L^-T = B Linv^T, in place (single column tile)
@@ -354,6 +393,14 @@ int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, in
            cudaStream_t st) {
   if (n <= 0 || nrhs <= 0) return 0;
   return trsm_rec<T>(trans, L, n, ldl, B, nrhs, ldb, dinv, 0, st);
+}
+
+// phase timing of one leaf launch (clock64 at phase boundaries), for tuning
+int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
+  GPK_TRY(leaf_attr<double>());
+  potrf_leaf_kernel<double><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg);
+  GPK_LAUNCH_OK();
+  return 0;
 }
 
 template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, cudaStream_t);

@@ -211,8 +211,8 @@ def tril_sumsq(A, *, scale: float = 1.0, out=None, accumulate: bool = False):
 # ---- elementwise -------------------------------------------------------------------------------------
 def axpby(a: float, X, b: float, Y):
     """Y = a X + b Y (2-D or 1-D)."""
-    if X.dim() == 1:
-        m, n, ldx, ldy = 1, X.shape[0], X.shape[0], Y.shape[0]
+    if X.dim() <= 1:
+        m, n, ldx, ldy = 1, X.numel(), X.numel(), Y.numel()
     else:
         (m, n), ldx, ldy = X.shape, _ld(X), _ld(Y)
     check(_lib.load().gpk_axpby(m, n, float(a), _p(X), ldx, float(b), _p(Y), ldy, dtype_code(X), _stream()),
@@ -244,8 +244,8 @@ def add_diag_(A, scalar: float = 0.0, vec=None):
 
 
 def fill(A, value: float):
-    if A.dim() == 1:
-        m, n, ld = 1, A.shape[0], A.shape[0]
+    if A.dim() <= 1:
+        m, n, ld = 1, A.numel(), A.numel()
     else:
         (m, n), ld = A.shape, _ld(A)
     check(_lib.load().gpk_fill(_p(A), m, n, ld, float(value), dtype_code(A), _stream()), "gpk_fill")

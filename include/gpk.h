@@ -222,6 +222,9 @@ GPK_API void gpk_launch_count_reset(void);
  * gpk_prof_read synchronises, writes summed milliseconds and launch counts for `n` classes and
  * clears the records. */
 #define GPK_PROF_CLASSES 5
+/* Tuning aid: runs ONE fp64 128x128 leaf (factor+invert) and stores clock64() at its phase
+ * boundaries into dbg[0..9] (device int64). */
+GPK_API int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* stream);
 GPK_API int gpk_prof_enable(int on);
 GPK_API int gpk_prof_read(double* ms, int64_t* launches, int n);
 
