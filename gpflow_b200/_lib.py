@@ -44,7 +44,7 @@ SIGNATURES = {
     "gpk_kbuild": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                            c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p]),
     "gpk_kdiag": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
-    "gpk_potrf_ws": (c_size_t, [c_int64, c_int]),
+    "gpk_potrf_ws": (c_size_t, [c_int64, c_int64, c_int]),
     "gpk_potrf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gpk_potrf_batched": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gpk_trsm_ws": (c_size_t, [c_int64, c_int]),

@@ -46,9 +46,11 @@ int gemm_any(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, cons
                        (float*)C, ldc, flags, st);
 }
 
-int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* dinv, cudaStream_t st) {
-  if (dtype == GPK_F64) return potrf_t<double>((double*)A, n, rows, lda, info, (double*)dinv, st);
-  return potrf_t<float>((float*)A, n, rows, lda, info, (float*)dinv, st);
+int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws, cudaStream_t st) {
+  const size_t tcb = potrf_tc_ws_bytes(n, rows, dtype);
+  void* tcws = tcb ? (char*)ws + align_up(dinv_bytes(n, dtype), 256) : nullptr;
+  if (dtype == GPK_F64) return potrf_t<double>((double*)A, n, rows, lda, info, (double*)ws, tcws, tcb, st);
+  return potrf_t<float>((float*)A, n, rows, lda, info, (float*)ws, nullptr, 0, st);
 }
 
 int trsm_any(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t nrhs, int64_t ldb, int dtype,
@@ -127,7 +129,7 @@ int gpk_kdiag(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const do
   return kdiag_impl(nodes, n_nodes, dims, ard, X, N, ldx, D, out, dtype, (cudaStream_t)stream);
 }
 
-size_t gpk_potrf_ws(int64_t n, int dtype) { return dinv_bytes(n, dtype); }
+size_t gpk_potrf_ws(int64_t n, int64_t rows, int dtype) { return potrf_ws_bytes(n, rows < n ? n : rows, dtype); }
 
 int gpk_potrf(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws, void* stream) {
   GPK_DTYPE_OK("potrf");
@@ -140,7 +142,7 @@ int gpk_potrf_batched(void* A, int64_t n, int64_t lda, int64_t stride, int batch
                       void* stream) {
   GPK_DTYPE_OK("potrf_batched");
   GPK_CHECK_ARG(A && ws && n >= 0 && lda >= n && batch >= 0, "potrf_batched: bad arguments");
-  for (int b = 0; b < batch; ++b)
+  for (int b = 0; b < batch; ++b)  // ws: gpk_potrf_ws(n, n, dtype), reused by every matrix of the batch
     GPK_TRY(potrf_any((char*)A + (size_t)b * stride * dtype_size(dtype), n, n, lda, dtype, info ? info + b : nullptr,
                       ws, (cudaStream_t)stream));
   return 0;

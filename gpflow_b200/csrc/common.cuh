@@ -74,7 +74,16 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
            const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st);
 
 template <typename T>
-int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, cudaStream_t st);
+int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
+            cudaStream_t st);
+
+// tcgen05 (int8-sliced fp64) symmetric rank-k update, gemm_tc.cu
+bool tc_enabled();
+int tc_slices();
+size_t syrk_tc_ws_bytes(int64_t m, int64_t K, int S);
+int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype);
 
 template <typename T>
 int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, int64_t ldb, const T* dinv,

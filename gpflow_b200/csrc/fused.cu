@@ -35,7 +35,7 @@ static GprWs gpr_layout(void* ws, int64_t N, int64_t P, int dtype) {
   GprWs w;
   w.lda = pad_ld(N);
   w.A = a.take((size_t)(N + P) * w.lda * dtype_size(dtype));
-  w.dinv = a.take(dinv_bytes(N, dtype));
+  w.dinv = a.take(potrf_ws_bytes(N, N + P, dtype));
   w.info = (int32_t*)a.take(256);
   w.bytes = a.off;
   return w;
@@ -86,8 +86,8 @@ static SgprWs sgpr_layout(void* ws, int64_t N, int64_t M, int64_t P, int dtype) 
   w.Kuu = a.take((size_t)M * w.ldm * ts);
   w.Kuf = a.take((size_t)M * w.ldn * ts);
   w.Bm = a.take((size_t)M * w.ldm * ts);
-  w.dinvL = a.take(dinv_bytes(M, dtype));
-  w.dinvB = a.take(dinv_bytes(M, dtype));
+  w.dinvL = a.take(potrf_ws_bytes(M, M, dtype));
+  w.dinvB = a.take(potrf_ws_bytes(M, M, dtype));
   w.kdiag = a.take((size_t)N * ts);
   w.c = a.take((size_t)M * P * ts);
   w.info = (int32_t*)a.take(256);
@@ -173,7 +173,7 @@ static SvgpWs svgp_layout(void* ws, int64_t B, int64_t M, int64_t P, int dtype) 
   w.ldb = pad_ld(B);
   w.Kuu = a.take((size_t)M * w.ldm * ts);
   w.A = a.take((size_t)M * w.ldb * ts);
-  w.dinv = a.take(dinv_bytes(M, dtype));
+  w.dinv = a.take(potrf_ws_bytes(M, M, dtype));
   w.v0 = a.take((size_t)B * ts);
   w.fvar = a.take((size_t)P * B * ts);   // [P][B]
   w.fmu = a.take((size_t)B * P * ts);    // [B][P]

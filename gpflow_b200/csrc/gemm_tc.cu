@@ -1,0 +1,390 @@
+// gemm_tc.cu — fp64 symmetric rank-k update on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//     C[m, n]  -=  A[m, K] * A[0:n, K]^T          (row-major fp64; the Cholesky trailing update)
+//
+// tcgen05.mma has no f64 kind (f16/tf32/f8f6f4/i8/mx* only), so the fp64 operands are split into
+// signed 7-bit digits with a per-row power-of-two scale (an Ozaki-style error-free splitting):
+//
+//     a_ik = 2^(e_i - 6) * sum_s 2^(-7 s) d_s(i,k),   d_s in [-64, 64]  (int8),  s = 0..S-1
+//
+// The digit products accumulate EXACTLY in int32 on the tensor cores (kind::i8); products with the
+// same weight s+t = g share one TMEM accumulator, so a CTA tile (128 x 64) holds S accumulators of
+// 64 columns (S = 7 -> 448 of the 512 TMEM columns) and issues S(S+1)/2 MMAs per 32-deep k-step.
+// The epilogue converts the S integer planes to fp64, recombines them with exact power-of-two
+// weights and the row/column scales, and applies C -= ... .  Truncation error per dot product is
+// bounded by K * S * 2^(-7S) relative to the row maxima (S = 7: ~2^-46 * K/64).
+//
+// Pipeline (per persistent CTA, 192 threads):
+//   warp 0   producer : cp.async.bulk (1-D TMA) of PRE-TILED digit planes global -> shared, mbarrier
+//   warp 1   issuer   : one elected lane issues tcgen05.mma (SS, no-swizzle K-major descriptors)
+//   warps 2-5 epilogue: tcgen05.ld TMEM -> registers, recombine, read-modify-write C
+// The slicing pre-pass (slice_rows_kernel) writes the digit planes directly in the canonical UMMA
+// shared-memory image (8x16-byte core matrices), so a stage is filled by plain bulk copies: no tensor
+// map, no swizzle to keep consistent between three places.
+//
+// Replaces the SYRK inside tf.linalg.cholesky (gpflow/models/gpr.py:102 etc.) for the large-K levels
+// of the recursion in potrf.cu; small-K levels and ragged shapes use the DMMA kernel of gemm.cu.
+#include "common.cuh"
+
+namespace gpk {
+
+constexpr int TC_BM = 128, TC_BN = 64, TC_KB = 32;   // CTA tile, bytes (= int8 elements) per k-step
+constexpr int TC_ATILE = TC_BM * TC_KB;              // 4096 B per digit plane of an A tile
+constexpr int TC_BTILE = TC_BN * TC_KB;              // 2048 B
+constexpr int TC_MAXS = 8;
+constexpr int TC_STAGES = 4;
+constexpr int TC_TMEM_COLS = 512;
+
+// ------------------------------------------------------------------------------------------------
+// slicing pre-pass: one warp per row
+// ------------------------------------------------------------------------------------------------
+// byte offset of element (row r in [0,128), k in [0,32)) inside one digit-plane tile:
+// canonical no-swizzle K-major UMMA layout ((8,n),2):((1,SBO),LBO) in 16-byte units, LBO=8, SBO=16
+__device__ __host__ __forceinline__ int tc_tile_off(int r, int k) {
+  return (r >> 3) * 256 + (k >> 4) * 128 + (r & 7) * 16 + (k & 15);
+}
+
+__global__ void __launch_bounds__(256)
+slice_rows_kernel(const double* __restrict__ P, int64_t m, int64_t mpad, int64_t K, int64_t ld, int S,
+                  int8_t* __restrict__ tiles, double* __restrict__ rowscale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= mpad) return;
+  const int KB = (int)(K / TC_KB);
+  const int64_t rb = r >> 7;
+  const int rr = (int)(r & 127);
+  int8_t* rowbase = tiles + (size_t)rb * KB * S * TC_ATILE;
+  const bool live = r < m;
+  double mx = 0.0;
+  if (live)
+    for (int64_t k = lane; k < K; k += 32) mx = fmax(mx, fabs(P[r * ld + k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int e = 0;
+  if (mx > 0.0 && mx < 1e300) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
+  const double sc = scalbn(1.0, -e + 6);          // x * 2^-e * 2^6
+  if (lane == 0) rowscale[r] = live ? scalbn(1.0, e - 6) : 0.0;
+  // each lane converts 4 consecutive k per iteration -> one 32-bit store per digit plane
+  for (int64_t k0 = lane * 4; k0 < K; k0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = live ? P[r * ld + k0 + q] * sc : 0.0;
+    const int kb = (int)(k0 / TC_KB), kk = (int)(k0 % TC_KB);
+    int8_t* tb = rowbase + (size_t)kb * S * TC_ATILE + tc_tile_off(rr, kk);
+    for (int s = 0; s < S; ++s) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double d = rint(v[q]);                 // |d| <= 64
+        v[q] = (v[q] - d) * 128.0;                   // exact: remainder, rescaled for the next digit
+        w |= (uint32_t)((int)d & 0xff) << (8 * q);
+      }
+      *reinterpret_cast<uint32_t*>(tb + (size_t)s * TC_ATILE) = w;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must abort the kernel, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > (1u << 26)) {
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B (next 16-byte k chunk),
+// SBO = 256 B (next group of 8 rows), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+struct TcTileIter {  // identical enumeration in every warp role
+  int64_t ntm, ntn;
+  int lower;
+  int64_t tm, tn, idx;
+  __device__ TcTileIter(int64_t m, int64_t n, int lower_) : lower(lower_), tm(0), tn(-1), idx(-1) {
+    ntm = (m + TC_BM - 1) / TC_BM;
+    ntn = (n + TC_BN - 1) / TC_BN;
+  }
+  __device__ int64_t ncols(int64_t t) const {
+    const int64_t lim = 2 * t + 2;  // column tiles touching the lower triangle of row tile t
+    return lower ? (lim < ntn ? lim : ntn) : ntn;
+  }
+  // advances to this CTA's next tile; false when exhausted
+  __device__ bool next() {
+    for (;;) {
+      ++tn;
+      while (tm < ntm && tn >= ncols(tm)) { ++tm; tn = 0; }
+      if (tm >= ntm) return false;
+      ++idx;
+      if (idx % gridDim.x == blockIdx.x) return true;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(192, 1)
+syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
+               int64_t ldc, int64_t m, int64_t n, int KB, int S, int lower, int* err) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  const uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
+  uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bar_area);  // full[4], empty[4], tmem_full, tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
+  const uint32_t tfull = smem_u32(bars + 2 * TC_STAGES), tempty = smem_u32(bars + 2 * TC_STAGES + 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      TcTileIter it(m, n, lower);
+      uint32_t st = 0, ph = 0;
+      while (it.next()) {
+        const int8_t* a_src = tiles + (size_t)it.tm * KB * S * TC_ATILE;
+        const int8_t* b_src = tiles + (size_t)(it.tn >> 1) * KB * S * TC_ATILE + (it.tn & 1) * TC_BTILE;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty0 + 8 * st, ph ^ 1, err, 101);
+          const uint32_t fb = full0 + 8 * st;
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
+          const uint32_t sb = sa + TC_MAXS * TC_ATILE;
+          bulk_g2s(sa, a_src + (size_t)kb * S * TC_ATILE, (uint32_t)S * TC_ATILE, fb);
+          for (int t = 0; t < S; ++t)
+            bulk_g2s(sb + t * TC_BTILE, b_src + ((size_t)kb * S + t) * TC_ATILE, TC_BTILE, fb);
+          if (++st == TC_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      TcTileIter it(m, n, lower);
+      uint32_t st = 0, ph = 0, tph = 0;
+      while (it.next()) {
+        mbar_wait(tempty, tph ^ 1, err, 102);  // epilogue has drained the accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full0 + 8 * st, ph, err, 103);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
+          const uint32_t sb = sa + TC_MAXS * TC_ATILE;
+          for (int s = 0; s < S; ++s) {
+            const uint64_t ad = tc_desc(sa + s * TC_ATILE);
+            for (int t = 0; t + s < S; ++t)
+              tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad, tc_desc(sb + t * TC_BTILE), TC_IDESC,
+                        (kb > 0 || s > 0) ? 1u : 0u);
+          }
+          tc_commit(empty0 + 8 * st);  // frees the stage once these MMAs have read it
+          if (++st == TC_STAGES) { st = 0; ph ^= 1; }
+        }
+        tc_commit(tfull);  // accumulators complete
+        tph ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (4 warps = 128 TMEM lanes) =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    TcTileIter it(m, n, lower);
+    uint32_t tph = 0;
+    while (it.next()) {
+      mbar_wait(tfull, tph, err, 104);
+      tc_fence_after();
+      const int64_t row = it.tm * TC_BM + q * 32 + lane;
+      const double rs = row < m ? rowscale[row] : 0.0;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        double acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+        double w = 1.0;
+        for (int g = 0; g < S; ++g) {
+          uint32_t v[32];
+          tc_ld32(lane_addr + (uint32_t)(g * TC_BN + half * 32), v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = fma((double)(int)v[c], w, acc[c]);
+          w *= 0.0078125;  // 2^-7
+        }
+        const int64_t col0 = it.tn * TC_BN + half * 32;
+        if (row < m) {
+          double* crow = C + row * ldc + col0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int64_t col = col0 + c;
+            if (col < n) crow[c] -= rs * rowscale[col] * acc[c];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+      tph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+size_t syrk_tc_ws_bytes(int64_t m, int64_t K, int S) {
+  const int64_t mpad = (m + TC_BM - 1) / TC_BM * TC_BM;
+  return align_up((size_t)mpad * K * S, 256) + align_up((size_t)mpad * sizeof(double), 256) + 256;
+}
+
+int tc_slices() {
+  static int s = -1;
+  if (s < 0) {
+    const char* e = getenv("GPK_TC_SLICES");
+    s = e ? atoi(e) : 7;
+    if (s < 4) s = 4;
+    if (s > TC_MAXS) s = TC_MAXS;
+  }
+  return s;
+}
+
+bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPK_FP64_ENGINE");
+    v = (e && (strcmp(e, "dmma") == 0 || strcmp(e, "simt") == 0)) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int tc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// C[m,n] -= A[m,K] A[0:n,K]^T (lower tiles only if `lower`); K % 32 == 0, n <= m.
+int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int S = tc_slices();
+  GPK_CHECK_ARG(K % TC_KB == 0 && K > 0 && n <= m, "syrk_tc: unsupported shape m=%lld n=%lld K=%lld", (long long)m,
+                (long long)n, (long long)K);
+  GPK_CHECK_ARG(ws && ws_bytes >= syrk_tc_ws_bytes(m, K, S), "syrk_tc: workspace too small");
+  const int64_t mpad = (m + TC_BM - 1) / TC_BM * TC_BM;
+  int8_t* tiles = (int8_t*)ws;
+  double* rowscale = (double*)((char*)ws + align_up((size_t)mpad * K * S, 256));
+  int* err = (int*)((char*)rowscale + align_up((size_t)mpad * sizeof(double), 256));
+  {
+    ProfScope ps(PROF_MISC, st);
+    slice_rows_kernel<<<(unsigned)((mpad + 7) / 8), 256, 0, st>>>(A, m, mpad, K, lda, S, tiles, rowscale);
+    GPK_LAUNCH_OK();
+  }
+  const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
+  static bool attr = false;
+  if (!attr) {
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  // number of tiles
+  const int64_t ntm = (m + TC_BM - 1) / TC_BM, ntn = (n + TC_BN - 1) / TC_BN;
+  int64_t ntiles = 0;
+  for (int64_t t = 0; t < ntm; ++t) ntiles += lower ? (2 * t + 2 < ntn ? 2 * t + 2 : ntn) : ntn;
+  int grid = tc_num_sms();
+  if (ntiles < grid) grid = (int)ntiles;
+  if (grid < 1) return 0;
+  ProfScope ps(PROF_GEMM, st);
+  syrk_i8_kernel<<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), S, lower, err);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace gpk

@@ -32,11 +32,16 @@ int transpose_impl(const void* A, int64_t m, int64_t n, int64_t lda, void* B, in
 // dtype-erased wrappers over the typed templates
 int gemm_any(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda, const void* B,
              int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags, cudaStream_t st);
-int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* dinv, cudaStream_t st);
+// ws = [dinv blocks | tcgen05 digit planes]; sized by potrf_ws_bytes(n, rows, dtype)
+int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws, cudaStream_t st);
+inline size_t potrf_ws_bytes(int64_t n, int64_t rows, int dtype);
 int trsm_any(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t nrhs, int64_t ldb, int dtype,
              const void* dinv, cudaStream_t st);
 int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype, cudaStream_t st);
 
 inline size_t dinv_bytes(int64_t n, int dtype) { return (size_t)((n + NB - 1) / NB) * NB * NB * dtype_size(dtype); }
+inline size_t potrf_ws_bytes(int64_t n, int64_t rows, int dtype) {
+  return align_up(dinv_bytes(n, dtype), 256) + potrf_tc_ws_bytes(n, rows, dtype);
+}
 
 }  // namespace gpk

@@ -326,9 +326,25 @@ static int leaf_attr() {
 
 static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
 
+constexpr int64_t TC_MIN_K = 256;  // below this the DMMA kernel wins (epilogue + slicing overhead)
+
 template <typename T>
-static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0,
-                     cudaStream_t st) {
+static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,
+                           size_t tcws_bytes, cudaStream_t st) {
+  if (sizeof(T) == 8 && tcws && tc_enabled() && K >= TC_MIN_K && K % 32 == 0 && n <= m &&
+      tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices()))
+    return syrk_tc_f64((double*)C, ldc, m, n, (const double*)P, ldp, K, 1, tcws, tcws_bytes, st);
+  return gemm_t<T>(0, 1, m, n, K, T(-1), P, ldp, P, ldp, T(1), C, ldc, GPK_GEMM_LOWER_ONLY, st);
+}
+
+size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
+  if (dtype != GPK_F64 || n < 2 * TC_MIN_K) return 0;
+  return syrk_tc_ws_bytes(rows, ((n / NB + 1) / 2) * NB, 8);
+}
+
+template <typename T>
+static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, void* tcws,
+                     size_t tcws_bytes, cudaStream_t st) {
   if (n <= NB) {
     T* dblk = dinv + (size_t)(col0 / NB) * NB * NB;
     {
@@ -341,19 +357,19 @@ static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, 
     return 0;
   }
   const int64_t n1 = split_point(n);
-  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, st));
+  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, tcws, tcws_bytes, st));
   // trailing update: A[n1:rows, n1:n] -= A[n1:rows, :n1] A[n1:n, :n1]^T  (lower tiles only)
-  GPK_TRY(gemm_t<T>(0, 1, rows - n1, n - n1, n1, T(-1), A + n1 * lda, lda, A + n1 * lda, lda, T(1),
-                    A + n1 * lda + n1, lda, GPK_GEMM_LOWER_ONLY, st));
-  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, st);
+  GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, tcws, tcws_bytes, st));
+  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, tcws, tcws_bytes, st);
 }
 
 template <typename T>
-int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, cudaStream_t st) {
+int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
+            cudaStream_t st) {
   if (n <= 0) return 0;
   GPK_TRY(leaf_attr<T>());
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-  return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, st);
+  return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, st);
 }
 
 template <typename T>
@@ -403,8 +419,8 @@ int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cuda
   return 0;
 }
 
-template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, cudaStream_t);
-template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, cudaStream_t);
+template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, void*, size_t, cudaStream_t);
+template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, void*, size_t, cudaStream_t);
 template int trtri_diag_t<float>(const float*, int64_t, int64_t, float*, cudaStream_t);
 template int trtri_diag_t<double>(const double*, int64_t, int64_t, double*, cudaStream_t);
 template int trsm_t<float>(int, const float*, int64_t, int64_t, float*, int64_t, int64_t, const float*, cudaStream_t);

@@ -126,7 +126,7 @@ def potrf(A, n: Optional[int] = None, *, check_info: bool = True):
     n = A.shape[1] if n is None else n
     lib = _lib.load()
     dc = dtype_code(A)
-    ws = scratch_bytes(lib.gpk_potrf_ws(n, dc))
+    ws = scratch_bytes(lib.gpk_potrf_ws(n, rows, dc))
     info = torch().empty((1,), dtype=torch().int32, device=A.device)
     check(lib.gpk_potrf(_p(A), n, rows, _ld(A), dc, _p(info), _p(ws), _stream()), "gpk_potrf")
     if check_info:
