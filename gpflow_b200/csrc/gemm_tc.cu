@@ -123,6 +123,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a converged warp (the rest of the warp keeps executing the same uniform control flow, so
+// descriptors / addresses stay in uniform registers and each tcgen05.mma is a single UTCIMMA issue
+// instead of an ELECT + R2UR waterfall per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -185,11 +197,12 @@ struct TcTileIter {  // identical enumeration in every warp role
   }
 };
 
+template <int S>
 __global__ void __launch_bounds__(192, 1)
 syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
-               int64_t ldc, int64_t m, int64_t n, int KB, int S, int lower, int* err) {
+               int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  const uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
+  constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
   uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bar_area);  // full[4], empty[4], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
@@ -219,51 +232,57 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== producer =====
-    if (lane == 0) {
-      TcTileIter it(m, n, lower);
-      uint32_t st = 0, ph = 0;
-      while (it.next()) {
-        const int8_t* a_src = tiles + (size_t)it.tm * KB * S * TC_ATILE;
-        const int8_t* b_src = tiles + (size_t)(it.tn >> 1) * KB * S * TC_ATILE + (it.tn & 1) * TC_BTILE;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(empty0 + 8 * st, ph ^ 1, err, 101);
+    // ===== producer (whole warp runs the loop; one elected lane issues the copies) =====
+    TcTileIter it(m, n, lower);
+    uint32_t st = 0, ph = 0;
+    while (it.next()) {
+      const int8_t* a_src = tiles + (size_t)it.tm * KB * S * TC_ATILE;
+      const int8_t* b_src = tiles + (size_t)(it.tn >> 1) * KB * S * TC_ATILE + (it.tn & 1) * TC_BTILE;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(empty0 + 8 * st, ph ^ 1, err, 101);
+        if (elect_one()) {
           const uint32_t fb = full0 + 8 * st;
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
           const uint32_t sb = sa + TC_MAXS * TC_ATILE;
           bulk_g2s(sa, a_src + (size_t)kb * S * TC_ATILE, (uint32_t)S * TC_ATILE, fb);
+#pragma unroll
           for (int t = 0; t < S; ++t)
             bulk_g2s(sb + t * TC_BTILE, b_src + ((size_t)kb * S + t) * TC_ATILE, TC_BTILE, fb);
-          if (++st == TC_STAGES) { st = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++st == TC_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      TcTileIter it(m, n, lower);
-      uint32_t st = 0, ph = 0, tph = 0;
-      while (it.next()) {
-        mbar_wait(tempty, tph ^ 1, err, 102);  // epilogue has drained the accumulators
+    // ===== MMA issuer (uniform control flow, one elected lane issues) =====
+    TcTileIter it(m, n, lower);
+    uint32_t st = 0, ph = 0, tph = 0;
+    const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+    while (it.next()) {
+      mbar_wait(tempty, tph ^ 1, err, 102);  // epilogue has drained the accumulators
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(full0 + 8 * st, ph, err, 103);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(full0 + 8 * st, ph, err, 103);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
-          const uint32_t sb = sa + TC_MAXS * TC_ATILE;
-          for (int s = 0; s < S; ++s) {
-            const uint64_t ad = tc_desc(sa + s * TC_ATILE);
+        const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
+        const uint64_t ad0 = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+        const uint64_t bd0 = ad0 + ((TC_MAXS * TC_ATILE) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+#pragma unroll
             for (int t = 0; t + s < S; ++t)
-              tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad, tc_desc(sb + t * TC_BTILE), TC_IDESC,
-                        (kb > 0 || s > 0) ? 1u : 0u);
-          }
+              tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
+                        bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
           tc_commit(empty0 + 8 * st);  // frees the stage once these MMAs have read it
-          if (++st == TC_STAGES) { st = 0; ph ^= 1; }
         }
-        tc_commit(tfull);  // accumulators complete
-        tph ^= 1;
+        __syncwarp();
+        if (++st == TC_STAGES) { st = 0; ph ^= 1; }
       }
+      if (elect_one()) tc_commit(tfull);  // accumulators complete
+      __syncwarp();
+      tph ^= 1;
     }
   } else {
     // ===== epilogue (4 warps = 128 TMEM lanes) =====
@@ -326,7 +345,7 @@ int tc_slices() {
   if (s < 0) {
     const char* e = getenv("GPK_TC_SLICES");
     s = e ? atoi(e) : 7;
-    if (s < 4) s = 4;
+    if (s < 6) s = 6;
     if (s > TC_MAXS) s = TC_MAXS;
   }
   return s;
@@ -371,7 +390,9 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
   static bool attr = false;
   if (!attr) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   // number of tiles
@@ -382,7 +403,12 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   if (ntiles < grid) grid = (int)ntiles;
   if (grid < 1) return 0;
   ProfScope ps(PROF_GEMM, st);
-  syrk_i8_kernel<<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), S, lower, err);
+  if (S == 6)
+    syrk_i8_kernel<6><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
+  else if (S == 7)
+    syrk_i8_kernel<7><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
+  else
+    syrk_i8_kernel<8><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
   GPK_LAUNCH_OK();
   return 0;
 }

@@ -371,6 +371,283 @@ __global__ void kdiag_kernel(const __grid_constant__ KProg prog, const T* __rest
   out[i] = s0;
 }
 
+
+// =============================================================================================
+// Fast path: ONE stationary leaf (RBF / Matern12 / Matern32 / Matern52 / Exponential) — the common
+// case and BASELINE config 2.  fp64 on B200 is compute-bound (exp(double) 835 Gop/s, sqrt 1164 Gop/s
+// measured vs 18.3 T DFMA/s), so this path
+//   * evaluates only lower-triangle tiles of a symmetric K and, for GPK_FULL, writes the mirrored
+//     tile through a shared-memory transpose (compute once, store twice: HBM-bound);
+//   * uses a table-driven exp (2^(j/64) table + degree-5 polynomial, ~12 DFMA instead of ~22) and a
+//     MUFU-seeded Newton square root (~9 instead of ~16);
+//   * launches a 1-D grid over the needed tiles only.
+// =============================================================================================
+__constant__ double c_exp2_tab[64];
+static double h_exp2_tab[64];
+static bool h_exp2_tab_ready = false;
+
+__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab) {  // x <= 0, tab in SHARED memory
+  if (x < -708.0) return 0.0;
+  const double t = x * 92.33248261689366;  // 64 / ln 2
+  const double sh = t + 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest integer in the low bits
+  const double kd = sh - 6755399441055744.0;
+  const int k = __double2loint(sh);
+  double r = fma(kd, -0.01083042468962958, x);           // ln2/64 hi (low 22 mantissa bits zero: kd*hi exact)
+  r = fma(kd, -6.619564634077006e-12, r);                // ln2/64 lo
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int j = k & 63, n = k >> 6;                      // k = 64 n + j, floor semantics for negative k
+  const double two_n = __longlong_as_double((long long)(n + 1023) << 52);
+  return tab[j] * p * two_n;  // lanes hit different entries: shared memory, never __constant__
+}
+__device__ __forceinline__ double fast_sqrt_pos(double x) {  // x >= 1e-36
+  double y = (double)__frsqrt_rn((float)x);  // MUFU.RSQ seed
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  double s = x * y;
+  return fma(0.5 * y, fma(-s, s, x), s);
+}
+
+template <typename T> struct FastMath;
+template <> struct FastMath<double> {
+  static __device__ __forceinline__ double exp_neg(double x, const double* tab) { return fast_exp_neg(x, tab); }
+  static __device__ __forceinline__ double sqrt_pos(double x) { return fast_sqrt_pos(x); }
+};
+template <> struct FastMath<float> {
+  static __device__ __forceinline__ float exp_neg(float x, const double*) { return __expf(x); }
+  static __device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
+};
+
+template <typename T, int TYPE>
+__device__ __forceinline__ T stationary_value(T r2, T var, const double* tab) {
+  using F = FastMath<T>;
+  if (TYPE == GPK_K_RBF) return var * F::exp_neg(fmin(T(-0.5) * r2, T(0)), tab);
+  const T r2c = fmax(r2, T(1e-36));
+  const T r = F::sqrt_pos(r2c);
+  if (TYPE == GPK_K_MATERN52) {
+    const T s5 = T(2.23606797749978969641);
+    return var * fma(T(5.0 / 3.0), r2c, fma(s5, r, T(1))) * F::exp_neg(-s5 * r, tab);
+  }
+  if (TYPE == GPK_K_MATERN32) {
+    const T s3 = T(1.73205080756887729353);
+    return var * fma(s3, r, T(1)) * F::exp_neg(-s3 * r, tab);
+  }
+  if (TYPE == GPK_K_MATERN12) return var * F::exp_neg(-r, tab);
+  return var * F::exp_neg(T(-0.5) * r, tab);  // Exponential
+}
+
+constexpr int KF_TS = KB_TILE + 1;  // transpose staging stride
+
+template <typename T, int TYPE>
+__global__ void __launch_bounds__(256)
+kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
+                   const T* __restrict__ X2, int64_t N2, int64_t ldx2, T* __restrict__ K, int64_t ldk, int mode,
+                   T diag_scalar, const T* __restrict__ diag_vec, int vec_ok) {
+  // mode: 0 rectangular (2-D tile index from the 1-D grid), 1 symmetric lower-only, 2 symmetric full (mirror)
+  extern __shared__ __align__(16) unsigned char kf_smem[];
+  T* sA = reinterpret_cast<T*>(kf_smem);            // [KB_KC][KB_TILE]
+  T* sB = sA + KB_KC * KB_TILE;                     // [KB_KC][KB_TILE]
+  T* sNa = sB + KB_KC * KB_TILE;                    // [KB_TILE]
+  T* sNb = sNa + KB_TILE;                           // [KB_TILE]
+  T* sT = sNb + KB_TILE;                            // [KB_TILE][KF_TS] transpose staging (mode 2)
+  __shared__ double s_tab[64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  if (tid < 64) s_tab[tid] = c_exp2_tab[tid];
+  int64_t by, bx;
+  if (mode == 0) {
+    const int64_t ntx = (N2 + KB_TILE - 1) / KB_TILE;
+    by = blockIdx.x / ntx;
+    bx = blockIdx.x % ntx;
+  } else {  // lower-triangle tile enumeration: t = by (by + 1) / 2 + bx, bx <= by
+    const int64_t t = blockIdx.x;
+    by = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (by * (by + 1) / 2 > t) --by;
+    while ((by + 1) * (by + 2) / 2 <= t) ++by;
+    bx = t - by * (by + 1) / 2;
+  }
+  const int64_t row0 = by * KB_TILE, col0 = bx * KB_TILE;
+  const bool sym = mode != 0;
+  const T* Xb = sym ? X : X2;
+  const int64_t ldb = sym ? ldx : ldx2;
+
+  T dots[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dots[r][c] = T(0);
+  if (tid < KB_TILE) { sNa[tid] = T(0); sNb[tid] = T(0); }
+  const int nd = prog.g_ndims[0];
+  for (int d0 = 0; d0 < nd; d0 += KB_KC) {
+    const int kc = min(KB_KC, nd - d0);
+    __syncthreads();
+    for (int e = tid; e < kc * KB_TILE; e += 256) {
+      const int d = e % kc, r = e / kc;
+      const int col = prog.dims[d0 + d];
+      const int64_t gr = row0 + r, gc = col0 + r;
+      const T a = gr < N ? X[gr * ldx + col] : T(0);
+      const T b = gc < N2 ? Xb[gc * ldb + col] : T(0);
+      sA[d * KB_TILE + r] = a * T(prog.w[d0 + d]);
+      sB[d * KB_TILE + r] = b;
+    }
+    __syncthreads();
+    if (tid < 2 * KB_TILE) {  // weighted squared norms, same expression for rows and columns
+      const int r = tid & (KB_TILE - 1);
+      const bool is_row = tid < KB_TILE;
+      const int64_t g = (is_row ? row0 : col0) + r;
+      const T* src = is_row ? X : Xb;
+      const int64_t lds = is_row ? ldx : ldb;
+      T acc = T(0);
+      if (g < (is_row ? N : N2))
+        for (int d = 0; d < kc; ++d) {
+          const T x = src[g * lds + prog.dims[d0 + d]];
+          acc = fma(T(prog.w[d0 + d]) * x, x, acc);
+        }
+      if (is_row) sNa[r] += acc; else sNb[r] += acc;
+    }
+    for (int d = 0; d < kc; ++d) {
+      T a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = sA[d * KB_TILE + ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = sB[d * KB_TILE + tx * 4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dots[r][c] = fma(a[r], b[c], dots[r][c]);
+    }
+  }
+  __syncthreads();
+
+  const T scale = T(prog.l_scale[0]), var = T(prog.l_var[0]);
+  T vals[16];
+  T na[4], nb[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { na[r] = sNa[ty * 4 + r]; nb[r] = sNb[tx * 4 + r]; }
+  // fully unrolled (no local array, 32-bit index math); the sum of norms is formed FIRST so that
+  // (i,j) and (j,i) round identically and a symmetric K comes out bit-symmetric
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const T sn = na[r] + nb[c];
+      const T r2 = scale * fma(T(-2), dots[r][c], sn);
+      vals[r * 4 + c] = stationary_value<T, TYPE>(r2, var, s_tab);
+    }
+  if (sym && bx == by) {  // diagonal shift: only diagonal tiles carry diagonal elements
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (ty * 4 + r == tx * 4 + c) {
+          const int64_t gi = row0 + ty * 4 + r;
+          vals[r * 4 + c] += diag_scalar + ((diag_vec && gi < N) ? diag_vec[gi] : T(0));
+        }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = row0 + ty * 4 + r;
+    if (gi < N) {
+      const int64_t gj0 = col0 + tx * 4;
+      T* dst = K + gi * ldk + gj0;
+      if (vec_ok && gj0 + 3 < N2) {
+        if (sizeof(T) == 8) {
+          reinterpret_cast<double2*>(dst)[0] = make_double2((double)vals[r * 4 + 0], (double)vals[r * 4 + 1]);
+          reinterpret_cast<double2*>(dst)[1] = make_double2((double)vals[r * 4 + 2], (double)vals[r * 4 + 3]);
+        } else {
+          reinterpret_cast<float4*>(dst)[0] =
+              make_float4((float)vals[r * 4 + 0], (float)vals[r * 4 + 1], (float)vals[r * 4 + 2], (float)vals[r * 4 + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gj0 + c < N2) dst[c] = vals[r * 4 + c];
+      }
+    }
+  }
+  if (mode == 2 && bx < by) {  // mirrored tile K[col0.., row0..] = tile^T, staged for coalesced rows
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sT[(tx * 4 + c) * KF_TS + ty * 4 + r] = vals[r * 4 + c];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int tr = ty + 16 * r;                   // row of the transposed tile
+      const int64_t gi = col0 + tr;
+      if (gi < N2) {
+        const int64_t gj0 = row0 + tx * 4;
+        T* dst = K + gi * ldk + gj0;
+        const T* src = sT + tr * KF_TS + tx * 4;
+        if (vec_ok && gj0 + 3 < N) {
+          if (sizeof(T) == 8) {
+            reinterpret_cast<double2*>(dst)[0] = make_double2((double)src[0], (double)src[1]);
+            reinterpret_cast<double2*>(dst)[1] = make_double2((double)src[2], (double)src[3]);
+          } else {
+            reinterpret_cast<float4*>(dst)[0] = make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (gj0 + c < N) dst[c] = src[c];
+        }
+      }
+    }
+  }
+}
+
+static bool fast_path_ok(const KProg& p) {
+  if (p.n_leaves != 1 || p.n_ops != 1 || p.n_groups != 1) return false;
+  const int t = p.l_type[0];
+  return t == GPK_K_RBF || t == GPK_K_MATERN12 || t == GPK_K_MATERN32 || t == GPK_K_MATERN52 || t == GPK_K_EXPONENTIAL;
+}
+
+template <typename T, int TYPE>
+static int kbuild_fast_go(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2,
+                          void* K, int64_t ldk, int mode, double diag_scalar, const void* diag_vec, int vec_ok,
+                          cudaStream_t st) {
+  const size_t smem = (size_t)(2 * KB_KC * KB_TILE + 2 * KB_TILE + KB_TILE * KF_TS) * sizeof(T);
+  static bool attr = false;
+  if (!attr) {
+    GPK_CUDA_OK(cudaFuncSetAttribute(kbuild_fast_kernel<T, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int64_t nty = (N + KB_TILE - 1) / KB_TILE, ntx = (N2 + KB_TILE - 1) / KB_TILE;
+  const int64_t ntiles = mode == 0 ? nty * ntx : nty * (nty + 1) / 2;
+  GPK_CHECK_ARG(ntiles < (1ll << 31), "kbuild: too many tiles");
+  kbuild_fast_kernel<T, TYPE><<<(unsigned)ntiles, 256, smem, st>>>(p, (const T*)X, N, ldx, (const T*)X2, N2, ldx2, (T*)K,
+                                                                    ldk, mode, (T)diag_scalar, (const T*)diag_vec, vec_ok);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T>
+static int kbuild_fast_launch(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2,
+                              int64_t ldx2, void* K, int64_t ldk, int lower, double diag_scalar, const void* diag_vec,
+                              cudaStream_t st) {
+  if (!h_exp2_tab_ready) {
+    for (int j = 0; j < 64; ++j) h_exp2_tab[j] = exp2((double)j / 64.0);
+    GPK_CUDA_OK(cudaMemcpyToSymbol(c_exp2_tab, h_exp2_tab, sizeof(h_exp2_tab)));
+    h_exp2_tab_ready = true;
+  }
+  ProfScope ps(PROF_KBUILD, st);
+  const int vec_ok = ((uintptr_t)K % 16 == 0) && ((ldk * sizeof(T)) % 16 == 0);
+  const int mode = p.symmetric ? (lower ? 1 : 2) : 0;
+#define GPK_KF(TY) return kbuild_fast_go<T, TY>(p, X, N, ldx, X2, N2, ldx2, K, ldk, mode, diag_scalar, diag_vec, vec_ok, st)
+  switch (p.l_type[0]) {
+    case GPK_K_RBF: GPK_KF(GPK_K_RBF);
+    case GPK_K_MATERN12: GPK_KF(GPK_K_MATERN12);
+    case GPK_K_MATERN32: GPK_KF(GPK_K_MATERN32);
+    case GPK_K_MATERN52: GPK_KF(GPK_K_MATERN52);
+    default: GPK_KF(GPK_K_EXPONENTIAL);
+  }
+#undef GPK_KF
+}
+
 template <typename T>
 static int kbuild_launch(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2,
                          int64_t ldx2, void* K, int64_t ldk, int lower, double diag_scalar, const void* diag_vec,
@@ -407,6 +684,12 @@ int kbuild_impl(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const 
   KProg p;
   GPK_TRY(compile_kprog(nodes, n_nodes, dims, ard, D, p));
   p.symmetric = sym ? 1 : 0;
+  static const bool no_fast = getenv("GPK_KBUILD_GENERIC") != nullptr;
+  if (fast_path_ok(p) && !no_fast) {
+    if (dtype == GPK_F64)
+      return kbuild_fast_launch<double>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);
+    return kbuild_fast_launch<float>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);
+  }
   if (dtype == GPK_F64)
     return kbuild_launch<double>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);
   return kbuild_launch<float>(p, X, N, ldx, X2, N2, ldx2, K, ldk, uplo == GPK_LOWER, diag_scalar, diag_vec, st);

@@ -31,7 +31,16 @@ template <> __device__ __forceinline__ float sqrt_t<float>(float x) { return sqr
 //    columns by shuffles.
 
 template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
-template <> __device__ __forceinline__ double rsqrt_t<double>(double x) { return rsqrt(x); }
+// fp32 MUFU.RSQ seed + two Newton steps in fp64 (relative error ~2^-52): ~2/3 of the latency of the
+// library rsqrt(), which sits on the serial pivot chain of the diagonal-block factorisation.
+template <> __device__ __forceinline__ double rsqrt_t<double>(double x) {
+  double y = (double)rsqrtf((float)x);
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
 template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rsqrtf(x); }
 
 // ---- 32x32 diagonal block Cholesky by one warp: lane i owns row i in registers ---------------------
@@ -121,29 +130,26 @@ __device__ __forceinline__ void mt_zero(T (&acc)[4][4]) {
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
 }
 
-// ---- off-diagonal 32x32 blocks of the inverse (diagonal blocks already inverted) --------------------
+// ---- off-diagonal blocks of the inverse (diagonal 32x32 blocks already inverted) ---------------------
 // Linv is stored TRANSPOSED in the upper triangle of S INCLUDING the diagonal: Linv[r][c] = S[c][r],
-// r >= c.  The strict lower triangle of S still holds L.  tmp: 3 * 32*32 scratch.
+// r >= c.  The strict lower triangle of S still holds L.  tmp: 4096-element scratch.
+// Block recursion  [A 0; C D]^-1 = [A^-1 0; -D^-1 C A^-1, D^-1]:
+//   level 32: inside each 64x64 diagonal block (2 independent pairs, 64 threads each, 2 products)
+//   level 64: the 64x64 block (rows 64.., cols 0..63) with all 256 threads (2 products of depth 64)
 template <typename T>
 __device__ void invert_offdiag_128(T* S, T* tmp) {
   const int tid = threadIdx.x;
-  const int pair = tid >> 6, sub = tid & 63;  // 64 threads (8x8, interleaved 4x4 micro-tiles) per block
-  const int tr = sub >> 3, tc = sub & 7;
-  // by block distance d:  Linv_IJ = -Linv_II * sum_{K=J}^{I-1} L_IK Linv_KJ
-  for (int d = 1; d < 4; ++d) {
-    const int npairs = 4 - d;
-    const int J = pair, I = pair + d;
-    T acc[4][4];
-    if (pair < npairs) {
+  T acc[4][4];
+  {  // ---- level 32: pairs (I,J) = (1,0) and (3,2)
+    const int pair = tid >> 6, sub = tid & 63, tr = sub >> 3, tc = sub & 7;
+    const int J = 2 * pair, I = J + 1;
+    if (pair < 2) {
       mt_zero(acc);
-      for (int K = J; K < I; ++K) {
-        const T* La = S + (I * 32 + tr) * LS + K * 32;           // L_IK rows tr + 8 i
-        const T* Lb = S + (J * 32 + tc) * LS + K * 32;           // Linv_KJ[k][c] = S[J*32+c][K*32+k]
-        const bool tri = K == J;
-        mt_acc<T>(acc, 0, 32,
-                  [&](int i, int k) { return La[i * 8 * LS + k]; },
-                  [&](int j, int k) { const T v = Lb[j * 8 * LS + k]; return (!tri || k >= tc + 8 * j) ? v : T(0); });
-      }
+      const T* La = S + (I * 32 + tr) * LS + J * 32;   // L_IJ rows tr + 8 i
+      const T* Lb = S + (J * 32 + tc) * LS + J * 32;   // Linv_JJ[k][c] = S[J*32+c][J*32+k], k >= c
+      mt_acc<T>(acc, 0, 32,
+                [&](int i, int k) { return La[i * 8 * LS + k]; },
+                [&](int j, int k) { const T v = Lb[j * 8 * LS + k]; return k >= tc + 8 * j ? v : T(0); });
       T* tp = tmp + pair * 1024;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -151,19 +157,43 @@ __device__ void invert_offdiag_128(T* S, T* tmp) {
         for (int j = 0; j < 4; ++j) tp[(tr + 8 * i) * 32 + tc + 8 * j] = acc[i][j];
     }
     __syncthreads();
-    if (pair < npairs) {
+    if (pair < 2) {
       const T* tp = tmp + pair * 1024;
-      const T* Li = S + (I * 32) * LS + I * 32 + tr;             // Linv_II[r][k] = S[I*32+k][I*32+r], r >= k
+      const T* Li = S + (I * 32) * LS + I * 32 + tr;   // Linv_II[r][k] = S[I*32+k][I*32+r], r >= k
       mt_zero(acc);
       mt_acc<T>(acc, 0, 32,
                 [&](int i, int k) { const T v = Li[k * LS + 8 * i]; return (tr + 8 * i >= k) ? v : T(0); },
                 [&](int j, int k) { return tp[k * 32 + tc + 8 * j]; });
-      // Linv[I*32+r][J*32+c] = -acc  ->  S[J*32+c][I*32+r]
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) S[(J * 32 + tc + 8 * j) * LS + I * 32 + tr + 8 * i] = -acc[i][j];
     }
+    __syncthreads();
+  }
+  {  // ---- level 64: X = -D^-1 (C A^-1), C = L[64:128, 0:64], A^-1 = Linv[0:64,0:64], D^-1 = Linv[64:,64:]
+    const int tr = tid >> 4, tc = tid & 15;            // 16 x 16 threads, rows tr + 16 i, cols tc + 16 j
+    mt_zero(acc);
+    const T* Ca = S + (64 + tr) * LS;                  // C[r][k] = S[64+r][k]
+    const T* Ab = S + tc * LS;                         // A^-1[k][c] = S[c][k], k >= c
+    mt_acc<T>(acc, 0, 64,
+              [&](int i, int k) { return Ca[i * 16 * LS + k]; },
+              [&](int j, int k) { const T v = Ab[j * 16 * LS + k]; return k >= tc + 16 * j ? v : T(0); });
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmp[(tr + 16 * i) * 64 + tc + 16 * j] = acc[i][j];
+    __syncthreads();
+    mt_zero(acc);
+    const T* Di = S + 64 * LS + 64 + tr;               // D^-1[r][k] = S[64+k][64+r], r >= k
+    mt_acc<T>(acc, 0, 64,
+              [&](int i, int k) { const T v = Di[k * LS + 16 * i]; return (tr + 16 * i >= k) ? v : T(0); },
+              [&](int j, int k) { return tmp[k * 64 + tc + 16 * j]; });
+    // Linv[64+r][c] = -acc  ->  S[c][64+r]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) S[(tc + 16 * j) * LS + 64 + tr + 16 * i] = -acc[i][j];
     __syncthreads();
   }
 }
@@ -203,7 +233,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   T* S = reinterpret_cast<T*>(leaf_smem);  // [128][129]
   T* ldiag = S + NB * LS;                  // [128] diagonal of L
-  T* tmp = ldiag + NB;                     // [3][32*32] scratch (panel staging / inverse products)
+  T* tmp = ldiag + NB;                     // 4096-element scratch (panel staging / inverse products)
   const int tid = threadIdx.x;
   const int tr = tid >> 3, tc = tid & 7;   // 32 x 8 thread grid, interleaved 4x4 micro-tiles
 
@@ -246,23 +276,30 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
       for (int e = tid; e < nr * 32; e += 256) S[(t0 + (e >> 5)) * LS + jb + (e & 31)] = tmp[e];
       __syncthreads();
       if (J == 0) GPK_DBG(4);
-      // trailing update, column blocks of 32: C[r][c] -= sum_k S[r][jb+k] S[c][jb+k], c <= r
-      for (int cb = t0; cb < NB; cb += 32) {
-        const int nib = (NB - cb) / 32;
-        mt_zero(acc);
-        const T* Ra = S + (cb + tr) * LS + jb;
-        const T* Rb = S + (cb + tc) * LS + jb;
-        mt_acc<T>(acc, 0, 32,
-                  [&](int i, int k) { return i < nib ? Ra[i * 32 * LS + k] : T(0); },
-                  [&](int j, int k) { return Rb[j * 8 * LS + k]; });
+      // trailing update by 32x32 block pairs (rb >= cb), 64 threads (8x8 interleaved 4x4 micro-tiles)
+      // per pair:  C[r][c] -= sum_k S[r][jb+k] S[c][jb+k]
+      {
+        const int nblk = nr / 32, npairs = nblk * (nblk + 1) / 2;
+        const int grp = tid >> 6, sub = tid & 63, ptr_ = sub >> 3, ptc = sub & 7;
+        for (int pr = grp; pr < npairs; pr += 4) {
+          int rbk = 0, rem = pr;
+          while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
+          const int cbk = rem;
+          const int R0 = t0 + rbk * 32, C0 = t0 + cbk * 32;
+          mt_zero(acc);
+          const T* Ra = S + (R0 + ptr_) * LS + jb;
+          const T* Rb = S + (C0 + ptc) * LS + jb;
+          mt_acc<T>(acc, 0, 32,
+                    [&](int i, int k) { return Ra[i * 8 * LS + k]; },
+                    [&](int j, int k) { return Rb[j * 8 * LS + k]; });
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nib)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int r = cb + tr + 32 * i, c = cb + tc + 8 * j;
+              const int r = R0 + ptr_ + 8 * i, c = C0 + ptc + 8 * j;
               if (c <= r) S[r * LS + c] -= acc[i][j];
             }
+        }
       }
       __syncthreads();
       if (J == 0) GPK_DBG(5);
@@ -309,7 +346,7 @@ trtri_diag_kernel(const T* __restrict__ L, int64_t ldl, int64_t n, T* __restrict
 }
 
 template <typename T>
-static size_t leaf_smem_bytes() { return (size_t)(NB * LS + NB + 3 * 1024) * sizeof(T); }
+static size_t leaf_smem_bytes() { return (size_t)(NB * LS + NB + 4096) * sizeof(T); }
 
 template <typename T>
 static int leaf_attr() {
@@ -326,7 +363,7 @@ static int leaf_attr() {
 
 static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
 
-constexpr int64_t TC_MIN_K = 256;  // below this the DMMA kernel wins (epilogue + slicing overhead)
+constexpr int64_t TC_MIN_K = 512;  // below this the DMMA kernel wins (epilogue + slicing overhead)
 
 template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,

@@ -232,3 +232,34 @@ def test_reductions(cuda_device, dtype):
         Fmu, Fvar, Yv = rng.standard_normal((40, 3)).astype(dtype), rng.random((40, 3)).astype(dtype), rng.standard_normal((40, 3)).astype(dtype)
         got = ops.gaussian_varexp_sum(ops.to_device(Fmu), ops.to_device(Fvar), ops.to_device(Yv), 0.3, scale=2.0)
         assert_allclose(to_np(got), 2.0 * O.gaussian_variational_expectations(Fmu.astype(np.float64), Fvar.astype(np.float64), Yv.astype(np.float64), 0.3).sum(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["rbf", "rbf_ard", "m12", "m32", "m52", "exp"])
+def test_kbuild_fast_path_modes(cuda_device, name, dtype):
+    """Single-stationary-leaf fast path: rectangular, symmetric full (mirrored tiles) and lower-only, ragged N,
+    far-apart points (exp underflow) and coincident points (the 1e-36 clip)."""
+    rng = np.random.default_rng(21)
+    N, N2, D = 333, 190, 5
+    X = rng.standard_normal((N, D)) * np.where(rng.random((N, 1)) < 0.1, 40.0 if dtype == np.float64 else 4.0, 1.0)  # outliers
+    X[5] = X[4]                                                                       # duplicate row
+    X2 = rng.standard_normal((N2, D))
+    X, X2 = X.astype(dtype), X2.astype(dtype)
+    with gpf.config.as_context(gpf.config.Config(float=dtype)):
+        ko, kp = build(EXPRS[name], D, [O, gpf.kernels])
+        Xd, X2d = ops.to_device(X), ops.to_device(X2)
+        t = tol_for(EXPRS[name], dtype)
+        full = to_np(kp(Xd))
+        ref = ko(X)
+        if dtype == np.float32:  # the coincident pair carries the reference formulation's own eps*|x|^2 noise
+            full[4, 5] = full[5, 4] = ref[4, 5] = ref[5, 4] = 0.0
+        assert_allclose(full, ref, **t)
+        bad = np.argwhere(full != full.T)
+        assert len(bad) == 0, f"asymmetric entries, first: {bad[:6].tolist()} count {len(bad)}"  # mirrored tiles
+        assert_allclose(to_np(kp(Xd, X2d)), ko(X, X2), **tol(dtype))
+        desc = gpf.kernels.compile_kernel(kp, D)
+        low = ops.full((N, N), -3.0, like=Xd)
+        ops.kbuild(desc, Xd, None, uplo=_lib.GPK_LOWER, diag_scalar=0.5, out=low)
+        il = np.tril_indices(N)
+        assert_allclose(to_np(low)[il], (ref + 0.5 * np.eye(N))[il], **t)
+        assert np.all(to_np(low)[:64, 64:] == -3.0)
