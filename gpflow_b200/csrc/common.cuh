@@ -68,10 +68,18 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// Head-first launch option for the Cholesky look-ahead: tiles of the first 128-column block of C are
+// processed first and each one increments *head_flag (release) when its stores are done, so the
+// next diagonal-block factorisation (spinning on the flag on a second stream) overlaps the rest.
+struct GemmOpts {
+  int* head_flag = nullptr;
+};
+
 // Internal (typed, unchecked) entry points shared between translation units.
 template <typename T>
 int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
-           const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st);
+           const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st,
+           const GemmOpts* opts = nullptr);
 
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
@@ -82,7 +90,7 @@ bool tc_enabled();
 int tc_slices();
 size_t syrk_tc_ws_bytes(int64_t m, int64_t K, int S);
 int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
-                void* ws, size_t ws_bytes, cudaStream_t st);
+                void* ws, size_t ws_bytes, cudaStream_t st, const GemmOpts* opts = nullptr);
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype);
 
 template <typename T>

@@ -70,8 +70,10 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(512, 1)
 gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                  const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                 int flags) {
-  const int64_t m0 = (int64_t)blockIdx.y * GB, n0 = (int64_t)blockIdx.x * GB;
+                 int flags, int* head_flag) {
+  // head_flag != nullptr: grid is (row tiles, column tiles) so column block 0 is dispatched first
+  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * GB;
+  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * GB;
   if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
   extern __shared__ __align__(16) double dsm[];
   double* sA = dsm;               // [2][DTILE]
@@ -181,6 +183,14 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
       }
     }
   }
+  if (head_flag && n0 == 0) {  // publish: this head tile is complete ([0] all head tiles, [1] diagonal tile)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(head_flag, 1);
+      if (m0 == 0) atomicAdd(head_flag + 1, 1);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,8 +201,9 @@ constexpr int SK = 8;
 template <typename T, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
-                 const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags) {
-  const int64_t m0 = (int64_t)blockIdx.y * GB, n0 = (int64_t)blockIdx.x * GB;
+                 const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, int* head_flag) {
+  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * GB;
+  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * GB;
   if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
   __shared__ __align__(16) T sA[2][SK][GB + 4];
   __shared__ __align__(16) T sB[2][SK][GB + 4];
@@ -303,6 +314,14 @@ gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t l
       *dst = beta != T(0) ? v + beta * *dst : v;
     }
   }
+  if (head_flag && n0 == 0) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(head_flag, 1);
+      if (m0 == 0) atomicAdd(head_flag + 1, 1);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,8 +401,8 @@ static bool fp64_simt() {
 
 template <typename T>
 static int launch_simt(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
-                       const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st) {
-#define GO(TA_, TB_) gemm_simt_kernel<T, TA_, TB_><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+                       const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st, int* hf) {
+#define GO(TA_, TB_) gemm_simt_kernel<T, TA_, TB_><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
   if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
   else if (ta && !tb) GO(true, false); else GO(true, true);
 #undef GO
@@ -393,7 +412,7 @@ static int launch_simt(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t 
 
 static int launch_dmma(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags,
-                       cudaStream_t st) {
+                       cudaStream_t st, int* hf) {
   const size_t smem = 4 * DTILE * sizeof(double);  // 80 KB
   static bool attr_done = false;
   if (!attr_done) {
@@ -403,7 +422,7 @@ static int launch_dmma(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t 
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-#define GO(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, 512, smem, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+#define GO(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, 512, smem, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
   if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
   else if (ta && !tb) GO(true, false); else GO(true, true);
 #undef GO
@@ -413,25 +432,27 @@ static int launch_dmma(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t 
 
 template <typename T>
 int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda, const T* B,
-           int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st) {
+           int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st, const GemmOpts* opts) {
   if (m <= 0 || n <= 0) return 0;
+  int* hf = opts ? opts->head_flag : nullptr;
   // skinny right-hand side: never when C aliases an operand row-block larger than one thread's reach
-  if (n <= SKN && !transb && flags == 0 && (const void*)C != (const void*)B && (const void*)C != (const void*)A) {
+  if (!hf && n <= SKN && !transb && flags == 0 && (const void*)C != (const void*)B && (const void*)C != (const void*)A) {
     ProfScope ps(PROF_SKINNY, st);
     return launch_skinny<T>(transa, m, (int)n, k, alpha, A, lda, B, ldb, beta, C, ldc, st);
   }
   ProfScope ps(PROF_GEMM, st);
   dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB));
-  GPK_CHECK_ARG(grid.y <= 65535, "gemm: m too large for the grid");
+  if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
+  GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
   if (sizeof(T) == 8 && !fp64_simt())
     return launch_dmma(transa, transb, grid, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
-                       (double)beta, (double*)C, ldc, flags, st);
-  return launch_simt<T>(transa, transb, grid, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st);
+                       (double)beta, (double*)C, ldc, flags, st, hf);
+  return launch_simt<T>(transa, transb, grid, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf);
 }
 
 template int gemm_t<float>(int, int, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t,
-                           float, float*, int64_t, int, cudaStream_t);
+                           float, float*, int64_t, int, cudaStream_t, const GemmOpts*);
 template int gemm_t<double>(int, int, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*,
-                            int64_t, double, double*, int64_t, int, cudaStream_t);
+                            int64_t, double, double*, int64_t, int, cudaStream_t, const GemmOpts*);
 
 }  // namespace gpk

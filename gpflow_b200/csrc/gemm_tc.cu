@@ -174,10 +174,12 @@ constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
                               ((uint32_t)(TC_BM >> 4) << 24);
 
 struct TcTileIter {  // identical enumeration in every warp role
+  // Order: pass 0 = the "head" tiles (first 128 columns: tn < 2) of every row tile, pass 1 = the rest,
+  // so the next diagonal block's inputs are complete early (look-ahead, see potrf.cu).
   int64_t ntm, ntn;
-  int lower;
+  int lower, pass;
   int64_t tm, tn, idx;
-  __device__ TcTileIter(int64_t m, int64_t n, int lower_) : lower(lower_), tm(0), tn(-1), idx(-1) {
+  __device__ TcTileIter(int64_t m, int64_t n, int lower_) : lower(lower_), pass(0), tm(0), tn(-1), idx(-1) {
     ntm = (m + TC_BM - 1) / TC_BM;
     ntn = (n + TC_BN - 1) / TC_BN;
   }
@@ -185,12 +187,22 @@ struct TcTileIter {  // identical enumeration in every warp role
     const int64_t lim = 2 * t + 2;  // column tiles touching the lower triangle of row tile t
     return lower ? (lim < ntn ? lim : ntn) : ntn;
   }
+  __device__ bool is_head() const { return pass == 0; }
   // advances to this CTA's next tile; false when exhausted
   __device__ bool next() {
     for (;;) {
       ++tn;
-      while (tm < ntm && tn >= ncols(tm)) { ++tm; tn = 0; }
-      if (tm >= ntm) return false;
+      for (;;) {
+        if (pass == 0) {
+          const int64_t lim = ncols(tm) < 2 ? ncols(tm) : 2;
+          if (tm < ntm && tn >= lim) { ++tm; tn = 0; continue; }
+          if (tm >= ntm) { pass = 1; tm = 0; tn = 2; continue; }
+        } else {
+          if (tm < ntm && tn >= ncols(tm)) { ++tm; tn = 2; continue; }
+          if (tm >= ntm) return false;
+        }
+        break;
+      }
       ++idx;
       if (idx % gridDim.x == blockIdx.x) return true;
     }
@@ -200,7 +212,7 @@ struct TcTileIter {  // identical enumeration in every warp role
 template <int S>
 __global__ void __launch_bounds__(192, 1)
 syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
-               int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err) {
+               int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err, int* head_flag) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
   uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE);
@@ -321,6 +333,14 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
       tc_fence_before();
       mbar_arrive(tempty);
       tph ^= 1;
+      if (head_flag && it.is_head()) {  // publish this head tile once all four epilogue warps stored it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicAdd(head_flag, 1);
+          if (it.tm == 0) atomicAdd(head_flag + 1, 1);  // tiles of the next diagonal block
+        }
+      }
     }
   }
 
@@ -373,8 +393,9 @@ static int tc_num_sms() {
 
 // C[m,n] -= A[m,K] A[0:n,K]^T (lower tiles only if `lower`); K % 32 == 0, n <= m.
 int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
-                void* ws, size_t ws_bytes, cudaStream_t st) {
+                void* ws, size_t ws_bytes, cudaStream_t st, const GemmOpts* opts) {
   const int S = tc_slices();
+  int* hf = opts ? opts->head_flag : nullptr;
   GPK_CHECK_ARG(K % TC_KB == 0 && K > 0 && n <= m, "syrk_tc: unsupported shape m=%lld n=%lld K=%lld", (long long)m,
                 (long long)n, (long long)K);
   GPK_CHECK_ARG(ws && ws_bytes >= syrk_tc_ws_bytes(m, K, S), "syrk_tc: workspace too small");
@@ -399,16 +420,16 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   const int64_t ntm = (m + TC_BM - 1) / TC_BM, ntn = (n + TC_BN - 1) / TC_BN;
   int64_t ntiles = 0;
   for (int64_t t = 0; t < ntm; ++t) ntiles += lower ? (2 * t + 2 < ntn ? 2 * t + 2 : ntn) : ntn;
-  int grid = tc_num_sms();
+  int grid = tc_num_sms() - (hf ? 1 : 0);  // look-ahead: leave one SM for the concurrent leaf kernel
   if (ntiles < grid) grid = (int)ntiles;
   if (grid < 1) return 0;
   ProfScope ps(PROF_GEMM, st);
   if (S == 6)
-    syrk_i8_kernel<6><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
+    syrk_i8_kernel<6><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
   else if (S == 7)
-    syrk_i8_kernel<7><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
+    syrk_i8_kernel<7><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
   else
-    syrk_i8_kernel<8><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err);
+    syrk_i8_kernel<8><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
   GPK_LAUNCH_OK();
   return 0;
 }

@@ -41,7 +41,7 @@ int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype,
 
 inline size_t dinv_bytes(int64_t n, int dtype) { return (size_t)((n + NB - 1) / NB) * NB * NB * dtype_size(dtype); }
 inline size_t potrf_ws_bytes(int64_t n, int64_t rows, int dtype) {
-  return align_up(dinv_bytes(n, dtype), 256) + potrf_tc_ws_bytes(n, rows, dtype);
+  return align_up(dinv_bytes(n, dtype), 256) + 256 /* look-ahead counter */ + potrf_tc_ws_bytes(n, rows, dtype);
 }
 
 }  // namespace gpk

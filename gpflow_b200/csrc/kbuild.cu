@@ -97,7 +97,7 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
       w.resize(nd_dims);
       for (int d = 0; d < nd_dims; ++d) {
         double a = ard[nd.ard_off + d];
-        w[d] = nd.op == GPK_K_LINEAR ? a : 1.0 / (a * a);
+        w[d] = nd.op == GPK_K_LINEAR ? a : 1.0 / a;  // stationary: X/l on BOTH sides (stationaries.py:77-79)
       }
       if (nd.op == GPK_K_LINEAR) p.l_var[l] = 1.0;
     } else if (nd.op != GPK_K_LINEAR) {
@@ -106,7 +106,8 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
     // find or create the group
     int g = -1;
     for (int c = 0; c < p.n_groups && g < 0; ++c) {
-      if (p.g_ndims[c] != nd_dims || (p.g_weighted[c] != 0) != (!w.empty())) continue;
+      const int wmode = w.empty() ? 0 : (nd.op == GPK_K_LINEAR ? 1 : 2);
+      if (p.g_ndims[c] != nd_dims || p.g_weighted[c] != wmode) continue;
       bool same = true;
       for (int d = 0; d < nd_dims && same; ++d) {
         int col = nd.n_dims > 0 ? dims[nd.dims_off + d] : d;
@@ -120,7 +121,7 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
       g = p.n_groups++;
       p.g_ndims[g] = nd_dims;
       p.g_off[g] = tot_dims;
-      p.g_weighted[g] = w.empty() ? 0 : 1;
+      p.g_weighted[g] = w.empty() ? 0 : (nd.op == GPK_K_LINEAR ? 1 : 2);  // 1: A side only, 2: both sides
       for (int d = 0; d < nd_dims; ++d) {
         int col = nd.n_dims > 0 ? dims[nd.dims_off + d] : d;
         GPK_CHECK_ARG(col >= 0 && col < D, "kbuild: active dim %d out of range [0,%lld)", col, (long long)D);
@@ -238,26 +239,20 @@ kbuild_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64
         const int64_t gr = row0 + r, gc = col0 + r;
         T a = gr < N ? X[gr * ldx + col] : T(0);
         T b = gc < N2 ? Xb[gc * ldb + col] : T(0);
-        sA[d][r] = a * T(prog.w[off + d0 + d]);
-        sB[d][r] = b;
+        const T wv = T(prog.w[off + d0 + d]);
+        sA[d][r] = a * wv;
+        sB[d][r] = prog.g_weighted[g] == 2 ? b * wv : b;
       }
       __syncthreads();
-      // norms of this chunk (weighted): threads 0..63 rows, 64..127 columns
+      // squared norms of the staged (scaled) rows / columns: same expression on both sides
       if (tid < 2 * KB_TILE) {
         const int r = tid & (KB_TILE - 1);
         T acc = T(0);
         if (tid < KB_TILE) {
-          for (int d = 0; d < kc; ++d) {
-            T a = sA[d][r];
-            T wv = T(prog.w[off + d0 + d]);
-            acc += wv != T(0) ? a * a / wv : T(0);
-          }
+          for (int d = 0; d < kc; ++d) { const T a = sA[d][r]; acc = fma(a, a, acc); }
           sNa[g][r] += acc;
         } else {
-          for (int d = 0; d < kc; ++d) {
-            T b = sB[d][r];
-            acc += T(prog.w[off + d0 + d]) * b * b;
-          }
+          for (int d = 0; d < kc; ++d) { const T b = sB[d][r]; acc = fma(b, b, acc); }
           sNb[g][r] += acc;
         }
       }
@@ -441,10 +436,92 @@ __device__ __forceinline__ T stationary_value(T r2, T var, const double* tab) {
   return var * F::exp_neg(T(-0.5) * r, tab);  // Exponential
 }
 
+// Four elements at a time, stage by stage: every arithmetic step is issued for the four independent
+// elements back to back, so the long dependent chains (sqrt: ~8, exp: ~12 fp64 ops) overlap instead of
+// each waiting out the fp64 latency alone.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int TYPE>
+__device__ __forceinline__ void stationary_value4(const double (&r2in)[4], double var, const double* __restrict__ tab,
+                                                  double (&out)[4]) {
+  double arg[4], pre[4];
+  if (TYPE == GPK_K_RBF) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { arg[q] = fmin(-0.5 * r2in[q], 0.0); pre[q] = var; }
+  } else {
+    double x[4], y[4], e[4], r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = fmax(r2in[q], 1e-36);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q] = (double)rsqrt_approx((float)x[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] = fma(-x[q] * y[q], y[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q] = fma(0.5 * y[q], e[q], y[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] = fma(-x[q] * y[q], y[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q] = fma(0.5 * y[q], e[q], y[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = x[q] * y[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = fma(0.5 * y[q], fma(-r[q], r[q], x[q]), r[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (TYPE == GPK_K_MATERN52) {
+        const double s5 = 2.23606797749978969641;
+        pre[q] = var * fma(5.0 / 3.0, x[q], fma(s5, r[q], 1.0));
+        arg[q] = -s5 * r[q];
+      } else if (TYPE == GPK_K_MATERN32) {
+        const double s3 = 1.73205080756887729353;
+        pre[q] = var * fma(s3, r[q], 1.0);
+        arg[q] = -s3 * r[q];
+      } else if (TYPE == GPK_K_MATERN12) {
+        pre[q] = var;
+        arg[q] = -r[q];
+      } else {
+        pre[q] = var;
+        arg[q] = -0.5 * r[q];
+      }
+    }
+  }
+  // exp(arg), arg <= 0
+  double sh[4], kd[4], rr[4], p[4];
+  int k[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sh[q] = fma(arg[q], 92.33248261689366, 6755399441055744.0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { kd[q] = sh[q] - 6755399441055744.0; k[q] = __double2loint(sh[q]); }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -0.01083042468962958, arg[q]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -6.619564634077006e-12, rr[q]);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p[q] = fma(rr[q], 8.3333333333333332e-03, 4.1666666666666664e-02);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 1.6666666666666666e-01);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 0.5);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 1.0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 1.0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double two_n = __longlong_as_double((long long)((k[q] >> 6) + 1023) << 52);
+    const double v = pre[q] * tab[k[q] & 63] * p[q] * two_n;
+    out[q] = arg[q] < -708.0 ? 0.0 : v;
+  }
+}
+
 constexpr int KF_TS = KB_TILE + 1;  // transpose staging stride
 
 template <typename T, int TYPE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
                    const T* __restrict__ X2, int64_t N2, int64_t ldx2, T* __restrict__ K, int64_t ldk, int mode,
                    T diag_scalar, const T* __restrict__ diag_vec, int vec_ok) {
@@ -491,23 +568,17 @@ kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, 
       const int64_t gr = row0 + r, gc = col0 + r;
       const T a = gr < N ? X[gr * ldx + col] : T(0);
       const T b = gc < N2 ? Xb[gc * ldb + col] : T(0);
-      sA[d * KB_TILE + r] = a * T(prog.w[d0 + d]);
-      sB[d * KB_TILE + r] = b;
+      const T wv = T(prog.w[d0 + d]);   // 1 or 1/lengthscale_d, applied to both sides
+      sA[d * KB_TILE + r] = a * wv;
+      sB[d * KB_TILE + r] = b * wv;
     }
     __syncthreads();
-    if (tid < 2 * KB_TILE) {  // weighted squared norms, same expression for rows and columns
+    if (tid < 2 * KB_TILE) {  // squared norms of the staged rows / columns, identical expression
       const int r = tid & (KB_TILE - 1);
-      const bool is_row = tid < KB_TILE;
-      const int64_t g = (is_row ? row0 : col0) + r;
-      const T* src = is_row ? X : Xb;
-      const int64_t lds = is_row ? ldx : ldb;
+      const T* src = tid < KB_TILE ? sA : sB;
       T acc = T(0);
-      if (g < (is_row ? N : N2))
-        for (int d = 0; d < kc; ++d) {
-          const T x = src[g * lds + prog.dims[d0 + d]];
-          acc = fma(T(prog.w[d0 + d]) * x, x, acc);
-        }
-      if (is_row) sNa[r] += acc; else sNb[r] += acc;
+      for (int d = 0; d < kc; ++d) { const T v = src[d * KB_TILE + r]; acc = fma(v, v, acc); }
+      if (tid < KB_TILE) sNa[r] += acc; else sNb[r] += acc;
     }
     for (int d = 0; d < kc; ++d) {
       T a[4], b[4];
@@ -531,13 +602,23 @@ kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, 
   // fully unrolled (no local array, 32-bit index math); the sum of norms is formed FIRST so that
   // (i,j) and (j,i) round identically and a symmetric K comes out bit-symmetric
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 4; ++r) {
+    if (sizeof(T) == 8) {
+      double r2[4], o[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const T sn = na[r] + nb[c];
-      const T r2 = scale * fma(T(-2), dots[r][c], sn);
-      vals[r * 4 + c] = stationary_value<T, TYPE>(r2, var, s_tab);
+      for (int c = 0; c < 4; ++c) r2[c] = (double)scale * fma(-2.0, (double)dots[r][c], (double)na[r] + (double)nb[c]);
+      stationary_value4<TYPE>(r2, (double)var, s_tab, o);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vals[r * 4 + c] = (T)o[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const T sn = na[r] + nb[c];
+        const T r2 = scale * fma(T(-2), dots[r][c], sn);
+        vals[r * 4 + c] = stationary_value<T, TYPE>(r2, var, s_tab);
+      }
     }
+  }
   if (sym && bx == by) {  // diagonal shift: only diagonal tiles carry diagonal elements
 #pragma unroll
     for (int r = 0; r < 4; ++r)

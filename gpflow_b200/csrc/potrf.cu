@@ -229,7 +229,7 @@ __device__ __forceinline__ void write_dinv(const T* S, T* __restrict__ dinv) {
 template <typename T>
 __global__ void __launch_bounds__(256, 1)
 potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base,
-                  long long* dbg) {
+                  long long* dbg, int* wait_flag, int wait_target) {
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   T* S = reinterpret_cast<T*>(leaf_smem);  // [128][129]
   T* ldiag = S + NB * LS;                  // [128] diagonal of L
@@ -238,6 +238,17 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   const int tr = tid >> 3, tc = tid & 7;   // 32 x 8 thread grid, interleaved 4x4 micro-tiles
 
 #define GPK_DBG(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+  if (wait_flag) {  // look-ahead: the trailing update still running on the main stream publishes its
+    if (tid == 0) { // head tiles (this block's inputs) through a counter; bounded spin, never a hang
+      unsigned spins = 0;
+      while (atomicAdd(wait_flag, 0) < wait_target) {
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
   GPK_DBG(0);
   load_lower_block<T>(S, A, lda, n);
   __syncthreads();
@@ -365,13 +376,67 @@ static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
 
 constexpr int64_t TC_MIN_K = 512;  // below this the DMMA kernel wins (epilogue + slicing overhead)
 
+// ---- look-ahead context ------------------------------------------------------------------------------
+// The trailing update U (main stream) and the next diagonal-block factorisation (side stream) overlap:
+// U processes the tiles of its first 128-column block first and counts them in `flag`; the leaf kernel
+// spins on that counter, so it runs while U is still working on the remaining tiles.
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_inputs = nullptr, ev_side = nullptr, ev_u = nullptr;
+  int* flag = nullptr;     // device counters (in the workspace): [0] head tiles done, [1] diagonal tiles done
+  int target = 0;
+  bool pending = false;
+  bool enabled = false;
+};
+
+static bool lookahead_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static int lookahead_init(LookAhead& la, int* flag) {
+  static cudaStream_t side[16] = {nullptr};
+  static cudaEvent_t evs[16][3] = {{nullptr}};
+  if (!lookahead_enabled() || !flag) return 0;
+  int dev = 0;
+  GPK_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return 0;
+  if (!side[dev]) {
+    GPK_CUDA_OK(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][0], cudaEventDisableTiming));
+    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][1], cudaEventDisableTiming));
+    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][2], cudaEventDisableTiming));
+  }
+  la.side = side[dev];
+  la.ev_inputs = evs[dev][0];
+  la.ev_side = evs[dev][1];
+  la.ev_u = evs[dev][2];
+  la.flag = flag;
+  la.enabled = true;
+  return 0;
+}
+
 template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,
-                           size_t tcws_bytes, cudaStream_t st) {
-  if (sizeof(T) == 8 && tcws && tc_enabled() && K >= TC_MIN_K && K % 32 == 0 && n <= m &&
-      tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices()))
-    return syrk_tc_f64((double*)C, ldc, m, n, (const double*)P, ldp, K, 1, tcws, tcws_bytes, st);
-  return gemm_t<T>(0, 1, m, n, K, T(-1), P, ldp, P, ldp, T(1), C, ldc, GPK_GEMM_LOWER_ONLY, st);
+                           size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
+  GemmOpts opts;
+  const bool use_tc = sizeof(T) == 8 && tcws && tc_enabled() && K >= TC_MIN_K && K % 32 == 0 && n <= m &&
+                      tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices());
+  if (la.enabled) {
+    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 2 * sizeof(int), st));
+    opts.head_flag = la.flag;
+    la.target = use_tc ? (n > 64 ? 2 : 1) : 1;  // tiles covering the next 128x128 diagonal block
+    GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
+    la.pending = true;
+  }
+  int rc;
+  if (use_tc)
+    rc = syrk_tc_f64((double*)C, ldc, m, n, (const double*)P, ldp, K, 1, tcws, tcws_bytes, st, &opts);
+  else
+    rc = gemm_t<T>(0, 1, m, n, K, T(-1), P, ldp, P, ldp, T(1), C, ldc, GPK_GEMM_LOWER_ONLY, st, &opts);
+  if (rc == 0 && la.enabled) GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));  // U complete
+  return rc;
 }
 
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
@@ -381,23 +446,39 @@ size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
 
 template <typename T>
 static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, void* tcws,
-                     size_t tcws_bytes, cudaStream_t st) {
+                     size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
   if (n <= NB) {
     T* dblk = dinv + (size_t)(col0 / NB) * NB * NB;
+    // look-ahead: run the leaf (and its panel solve) on the side stream, gated by U's head-tile counter
+    cudaStream_t ls = st;
+    int* wf = nullptr;
+    int wt = 0;
+    if (la.pending) {
+      GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_inputs, 0));
+      ls = la.side;
+      wf = la.flag + 1;  // the leaf needs only the diagonal block of U's output
+      wt = la.target;
+    }
     {
-      ProfScope ps(PROF_LEAF, st);
-      potrf_leaf_kernel<T><<<1, 256, leaf_smem_bytes<T>(), st>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr);
+      ProfScope ps(PROF_LEAF, ls);
+      potrf_leaf_kernel<T><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
       GPK_LAUNCH_OK();
     }
+    if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
     if (rows > n)  // rows below: X = B L^-T = B Linv^T, in place (single column tile)
-      GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, st));
+      GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, ls));
+    if (la.pending) {
+      GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
+      GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));  // main stream joins (it also still holds U)
+      la.pending = false;
+    }
     return 0;
   }
   const int64_t n1 = split_point(n);
-  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, tcws, tcws_bytes, st));
+  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, tcws, tcws_bytes, la, st));
   // trailing update: A[n1:rows, n1:n] -= A[n1:rows, :n1] A[n1:n, :n1]^T  (lower tiles only)
-  GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, tcws, tcws_bytes, st));
-  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, tcws, tcws_bytes, st);
+  GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, tcws, tcws_bytes, la, st));
+  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, tcws, tcws_bytes, la, st);
 }
 
 template <typename T>
@@ -406,7 +487,11 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   if (n <= 0) return 0;
   GPK_TRY(leaf_attr<T>());
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-  return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, st);
+  LookAhead la;
+  // the look-ahead counter lives in the last 256 bytes of the dinv area's alignment slack (see potrf_ws_bytes)
+  int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(dinv) + (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(T));
+  if (n > NB) GPK_TRY(lookahead_init(la, flag));
+  return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, la, st);
 }
 
 template <typename T>
@@ -451,7 +536,7 @@ int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, in
 // phase timing of one leaf launch (clock64 at phase boundaries), for tuning
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
   GPK_TRY(leaf_attr<double>());
-  potrf_leaf_kernel<double><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg);
+  potrf_leaf_kernel<double><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0);
   GPK_LAUNCH_OK();
   return 0;
 }
