@@ -321,6 +321,8 @@ def run_ours(args):
         import torch.distributed as dist_
 
         dist = dist_
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gpflow_b200 import _lib
 

@@ -251,6 +251,8 @@ def test_kbuild_fast_path_modes(cuda_device, name, dtype):
         t = tol_for(EXPRS[name], dtype)
         if dtype == np.float32:  # eps * |x|^2 noise of the norm-expansion distance with |x| up to ~7
             t = dict(rtol=max(t["rtol"], 1e-4), atol=max(t["atol"], 1e-4))
+        elif name in ("m12", "exp"):  # sqrt(eps * |x|^2) with the |x|~18 outliers
+            t = dict(rtol=1e-6, atol=1e-6)
         full = to_np(kp(Xd))
         ref = ko(X)
         chk, rchk = full.copy(), ref.copy()

@@ -329,3 +329,48 @@ def test_c2_full_size_factor_residual(cuda_device):
     num = float(ops.reduce(ops.SUMSQ, R, R.numel())) ** 0.5
     den = float(ops.reduce(ops.SUMSQ, K, K.numel())) ** 0.5
     assert num / den < 1e-13
+
+
+def _gold_full():
+    path = os.path.join(HERE, "golden", "golden_full.json")
+    if not os.path.exists(path):
+        pytest.skip("golden_full.json not generated")
+    return json.load(open(path))
+
+
+def test_c3_full_size_sgpr_elbo_golden(cuda_device):
+    """BASELINE config 3 at full size (N=100000, M=1024, D=16): fp32 within 1e-3 and fp64 within 1e-8 of the
+    fp64 golden scalar."""
+    gold = _gold_full()["c3_elbo_N100000_M1024_D16_f64_jitter1e-4"]
+    d = O.make_data(3, 100000, 16, 1, M=1024)
+    with gpf.config.as_context(gpf.config.Config(float=np.float32, jitter=1e-4)):
+        m = gpf.models.SGPR((d["X"], d["Y"]), product_kernel(3, 16), d["Z"], noise_variance=0.1)
+        assert_allclose(float(m.elbo()), gold, rtol=1e-3)
+    with gpf.config.as_context(gpf.config.Config(float=np.float64, jitter=1e-4)):
+        m = gpf.models.SGPR((d["X"], d["Y"]), product_kernel(3, 16), d["Z"], noise_variance=0.1)
+        assert_allclose(float(m.elbo()), gold, rtol=1e-8)
+
+
+def test_c4_full_size_svgp_elbo_golden(cuda_device):
+    """BASELINE config 4 at full size (B=4096, M=2048, P=8, D=16, num_data=1e6), first minibatch."""
+    gold = _gold_full()["c4_elbo_N1e6_B4096_M2048_P8_D16_f64_jitter1e-4_batch0"]
+    d = O.make_data(4, 1000000, 16, 8, M=2048)
+    q_mu, q_sqrt = O.make_q(4, 2048, 8)
+    Xb, Yb = d["X"][:4096], d["Y"][:4096]
+    for dtype, rtol in ((np.float32, 1e-3), (np.float64, 1e-8)):
+        with gpf.config.as_context(gpf.config.Config(float=dtype, jitter=1e-4)):
+            m = gpf.models.SVGP(product_kernel(4, 16), gpf.likelihoods.Gaussian(0.1), d["Z"], num_latent_gps=8, q_mu=q_mu,
+                                q_sqrt=q_sqrt, whiten=True, num_data=1000000)
+            assert_allclose(float(m.elbo((Xb, Yb))), gold, rtol=rtol)
+            if dtype == np.float64:  # latent sharding over 8 "GPUs" at full size
+                parts = [float(m.elbo((Xb, Yb), latent_range=(p, p + 1))) for p in range(8)]
+                assert_allclose(sum(parts), gold, rtol=1e-8)
+
+
+def test_c5_full_size_multi_output_lml_golden(cuda_device):
+    gold = _gold_full()["c5_lml_N4096_D32_P4_f64"]
+    d = O.make_data(5, 4096, 32, 4)
+    ks = product_c5_kernels(32)
+    total = sum(float(gpf.models.GPR((d["X"], d["Y"][:, p:p + 1]), ks[p], noise_variance=0.1).log_marginal_likelihood())
+                for p in range(4))
+    assert_allclose(total, gold, rtol=1e-8)
