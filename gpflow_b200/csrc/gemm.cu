@@ -338,27 +338,45 @@ gemm_skinny_kernel(int64_t m, int n, int64_t k, T alpha, const T* A, int64_t lda
 #pragma unroll
   for (int j = 0; j < SKN; ++j) acc[j] = T(0);
   if (!TA) {
-    // one warp per output row; lanes stride over k (row of A contiguous)
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= m) return;
+    // one CTA (8 warps) per output row: the warps split k, lanes stride over it (row of A contiguous),
+    // 4 independent loads in flight per lane; partial sums meet in shared memory
+    __shared__ T red[8][SKN];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x;
     const T* arow = A + i * lda;
-    for (int64_t kk = lane; kk < k; kk += 32) {
-      const T a = arow[kk];
-      const T* brow = B + kk * ldb;
+    const int64_t kchunk = (k + 7) / 8, k0 = wp * kchunk, k1 = min(k, k0 + kchunk);
+    int64_t kk = k0 + lane;
+    for (; kk + 96 < k1; kk += 128) {
+      const T a0 = arow[kk], a1 = arow[kk + 32], a2 = arow[kk + 64], a3 = arow[kk + 96];
 #pragma unroll
       for (int j = 0; j < SKN; ++j)
-        if (j < n) acc[j] = fma(a, brow[j], acc[j]);
+        if (j < n) {
+          acc[j] = fma(a0, B[kk * ldb + j], acc[j]);
+          acc[j] = fma(a1, B[(kk + 32) * ldb + j], acc[j]);
+          acc[j] = fma(a2, B[(kk + 64) * ldb + j], acc[j]);
+          acc[j] = fma(a3, B[(kk + 96) * ldb + j], acc[j]);
+        }
+    }
+    for (; kk < k1; kk += 32) {
+      const T a = arow[kk];
+#pragma unroll
+      for (int j = 0; j < SKN; ++j)
+        if (j < n) acc[j] = fma(a, B[kk * ldb + j], acc[j]);
     }
 #pragma unroll
     for (int j = 0; j < SKN; ++j)
       if (j < n) {
-        T s = warp_sum(acc[j]);
-        if (lane == 0) {
-          T* dst = C + i * ldc + j;
-          *dst = beta != T(0) ? alpha * s + beta * *dst : alpha * s;
-        }
+        const T s = warp_sum(acc[j]);
+        if (lane == 0) red[wp][j] = s;
       }
+    __syncthreads();
+    if (threadIdx.x < n) {
+      T s = T(0);
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+      T* dst = C + i * ldc + threadIdx.x;
+      *dst = beta != T(0) ? alpha * s + beta * *dst : alpha * s;
+    }
   } else {
     // A stored [k][m]: one thread per output row, coalesced across threads
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,7 +401,7 @@ template <typename T>
 static int launch_skinny(int ta, int64_t m, int n, int64_t k, T alpha, const T* A, int64_t lda, const T* B, int64_t ldb,
                          T beta, T* C, int64_t ldc, cudaStream_t st) {
   if (!ta)
-    gemm_skinny_kernel<T, false><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    gemm_skinny_kernel<T, false><<<(unsigned)m, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   else
     gemm_skinny_kernel<T, true><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   GPK_LAUNCH_OK();
@@ -440,6 +458,9 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
     ProfScope ps(PROF_SKINNY, st);
     return launch_skinny<T>(transa, m, (int)n, k, alpha, A, lda, B, ldb, beta, C, ldc, st);
   }
+  if (sizeof(T) == 4 && !hf && gemm_tf32_eligible(m, n, k, A, B, C, flags))
+    return gemm_tf32(transa, transb, m, n, k, (float)alpha, (const float*)A, lda, (const float*)B, ldb, (float)beta,
+                     (float*)C, ldc, flags, st);
   ProfScope ps(PROF_GEMM, st);
   dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB));
   if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first

@@ -62,3 +62,46 @@ def test_gpr_lml_tc_vs_dmma_engines(cuda_device):
     lml = float(m.log_marginal_likelihood())
     ref = O.gpr_log_marginal_likelihood(d["X"], d["Y"], O.Matern52(lengthscales=np.sqrt(8.0)), 0.1)
     assert_allclose(lml, ref, rtol=1e-9)
+
+
+# ---- fp32 GEMM on tcgen05 kind::tf32 (3xTF32) ----------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(512, 768, 640), (300, 1000, 777), (1024, 1024, 20000), (128, 5000, 128)])
+def test_gemm_tf32_tcgen05_matches_fp64(cuda_device, ta, tb, m, n, k):
+    """Shapes above the eligibility threshold run on the tensor cores; the 3xTF32 compensation keeps fp32
+    accuracy (error ~ sqrt(k) * 2^-23 relative to |a||b|).  (1024,1024,20000) exercises split-K atomics."""
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((k, m) if ta else (m, k)).astype(np.float32)
+    B = rng.standard_normal((n, k) if tb else (k, n)).astype(np.float32)
+    C = rng.standard_normal((m, n)).astype(np.float32)
+    ref = 0.7 * (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64) - 0.3 * C
+    with gpf.config.as_context(gpf.config.Config(float=np.float32)):
+        Cd = ops.to_device(C.copy())
+        ops.gemm(ops.to_device(A), ops.to_device(B), transa=bool(ta), transb=bool(tb), alpha=0.7, beta=-0.3, out=Cd)
+    err = np.abs(to_np(Cd) - ref).max()
+    assert err < 4e-6 * np.sqrt(k) * 3.0, err     # plain TF32 (10-bit mantissa) would be ~1e-3 * sqrt(k)
+
+
+def test_gemm_tf32_flags(cuda_device):
+    from gpflow_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    with gpf.config.as_context(gpf.config.Config(float=np.float32)):
+        m, k = 1500, 900
+        A = rng.standard_normal((m, k)).astype(np.float32)
+        C = ops.full((m, m), 5.0, dtype=np.float32)
+        ops.gemm(ops.to_device(A), ops.to_device(A), transb=True, out=C, flags=_lib.GPK_GEMM_LOWER_ONLY)
+        ref = A.astype(np.float64) @ A.T.astype(np.float64)
+        il = np.tril_indices(m)
+        assert np.all(np.abs(to_np(C)[il] - ref[il]) < 2e-6 * np.abs(ref[il]) + 2e-4)
+        assert np.all(to_np(C)[:128, 256:] == 5.0)           # tiles strictly above the diagonal untouched
+        kq, n = 1100, 2000
+        Q = rng.standard_normal((kq, kq)).astype(np.float32)
+        Bm = rng.standard_normal((kq, n)).astype(np.float32)
+        ref = np.tril(Q).T.astype(np.float64) @ Bm.astype(np.float64)
+        got = ops.gemm(ops.to_device(Q), ops.to_device(Bm), transa=True, flags=_lib.GPK_GEMM_A_LOWER)
+        assert np.all(np.abs(to_np(got) - ref) < 2e-6 * np.abs(ref) + 2e-4)
+        v = ops.full((n,), 1.5, dtype=np.float32)
+        ops.gemm(ops.to_device(Q), ops.to_device(Bm), transa=True, out=v,
+                 flags=_lib.GPK_GEMM_A_LOWER | _lib.GPK_GEMM_COLSUMSQ)
+        assert_allclose(to_np(v), 1.5 + (ref ** 2).sum(0), rtol=2e-5)
