@@ -201,9 +201,20 @@ class OurArm:
             return self.models[0].elbo()
         if len(self.models) == 1:
             return self.models[0].log_marginal_likelihood()
+        # independent outputs: one CUDA stream per model so the (latency-bound) factorisations overlap
+        T = ops.torch()
+        if not hasattr(self, "_streams"):
+            self._streams = [T.cuda.Stream() for _ in self.models]
+        cur = T.cuda.current_stream()
+        vals = []
+        for m, s_ in zip(self.models, self._streams):
+            s_.wait_stream(cur)
+            with T.cuda.stream(s_):
+                vals.append(m.log_marginal_likelihood())
         acc = ops.zeros_scalar(1)
-        for m in self.models:
-            ops.axpby(1.0, m.log_marginal_likelihood().reshape(1), 1.0, acc)
+        for v, s_ in zip(vals, self._streams):
+            cur.wait_stream(s_)
+            ops.axpby(1.0, v.reshape(1), 1.0, acc)
         return acc[0]
 
     def eval_e2e(self, pinned):

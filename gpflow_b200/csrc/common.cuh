@@ -74,6 +74,19 @@ __device__ __forceinline__ T warp_sum(T v) {
 struct GemmOpts {
   int* head_flag = nullptr;
 };
+// head_flag[1] counts the finished part of C's leading 128x128 block in 32x32 units, so kernels with
+// different tile shapes publish comparable progress; the waiting leaf needs diag_units_total(m, n).
+__host__ __device__ inline int diag_units_total(long long m, long long n) {
+  const long long a = m < 128 ? m : 128, b = n < 128 ? n : 128;
+  return (int)(((a + 31) / 32) * ((b + 31) / 32));
+}
+__device__ inline int diag_units_tile(long long m0, long long n0, int bm, int bn, long long m, long long n) {
+  if (m0 >= 128 || n0 >= 128) return 0;
+  const long long a = (m < 128 ? m : 128) - m0, b = (n < 128 ? n : 128) - n0;
+  const long long ra = a < bm ? a : bm, rb = b < bn ? b : bn;
+  if (ra <= 0 || rb <= 0) return 0;
+  return (int)(((ra + 31) / 32) * ((rb + 31) / 32));
+}
 
 // Internal (typed, unchecked) entry points shared between translation units.
 template <typename T>

@@ -35,17 +35,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Loads this thread's share of one operand chunk into registers.
+// Loads this thread's share of one operand chunk (ROWS x 16) into registers.
 // STORED_KMINOR: global operand is [rows][k] (k contiguous); else [k][rows] (rows contiguous).
 // tri: 0 none; 1 = stored matrix is lower triangular (zero where stored_col > stored_row).
-template <bool STORED_KMINOR>
-__device__ __forceinline__ void dload(double (&reg)[4], const double* P, int64_t ld, int64_t r0,
+template <bool STORED_KMINOR, int ROWS, int NT>
+__device__ __forceinline__ void dload(double (&reg)[ROWS * DK / NT], const double* P, int64_t ld, int64_t r0,
                                       int64_t nrows, int64_t k0, int64_t kend, int tid, int tri) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int e = tid + i * 512;  // 0..2047
+  for (int i = 0; i < ROWS * DK / NT; ++i) {
+    const int e = tid + i * NT;
     int rr, kk;
-    if (STORED_KMINOR) { kk = e % DK; rr = e / DK; } else { rr = e % GB; kk = e / GB; }
+    if (STORED_KMINOR) { kk = e % DK; rr = e / DK; } else { rr = e % ROWS; kk = e / ROWS; }
     const int64_t gr = r0 + rr, gk = k0 + kk;
     double v = 0.0;
     if (gr < nrows && gk < kend) {
@@ -56,40 +56,47 @@ __device__ __forceinline__ void dload(double (&reg)[4], const double* P, int64_t
   }
 }
 
-template <bool STORED_KMINOR>
-__device__ __forceinline__ void dstore(const double (&reg)[4], double* __restrict__ S, int tid) {
+template <bool STORED_KMINOR, int ROWS, int NT>
+__device__ __forceinline__ void dstore(const double (&reg)[ROWS * DK / NT], double* __restrict__ S, int tid) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int e = tid + i * 512;
+  for (int i = 0; i < ROWS * DK / NT; ++i) {
+    const int e = tid + i * NT;
     if (STORED_KMINOR) { const int kk = e % DK, rr = e / DK; S[rr * DS_K + kk] = reg[i]; }
-    else { const int rr = e % GB, kk = e / GB; S[kk * DS_M + rr] = reg[i]; }
+    else { const int rr = e % ROWS, kk = e / ROWS; S[kk * (ROWS + 4) + rr] = reg[i]; }
   }
 }
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(512, 1)
+// CTA tile BM x BN (multiples of 32), one warp per 32x32 sub-tile.  128x128 is the throughput shape;
+// 64x128 / 32x128 / 128x64 / 128x32 spread the narrow GEMMs of the recursion (a single 128-wide block
+// column or row: panel solves, K=128 updates) over more SMs — one SM needs >= 17 us for a 128^3 tile.
+template <bool TA, bool TB, int BM, int BN>
+__global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32)
 gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                  const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                  int flags, int* head_flag) {
+  constexpr int NT = (BM / 32) * (BN / 32) * 32;
+  constexpr int WN = BN / 32;
+  constexpr int ATILE = BM * DS_K > DK * (BM + 4) ? BM * DS_K : DK * (BM + 4);
+  constexpr int BTILE = BN * DS_K > DK * (BN + 4) ? BN * DS_K : DK * (BN + 4);
   // head_flag != nullptr: grid is (row tiles, column tiles) so column block 0 is dispatched first
-  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * GB;
-  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * GB;
-  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
+  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * BM;
+  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * BN;
+  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + BM - 1) return;
   extern __shared__ __align__(16) double dsm[];
-  double* sA = dsm;               // [2][DTILE]
-  double* sB = dsm + 2 * DTILE;   // [2][DTILE]
-  __shared__ double s_col[GB];
+  double* sA = dsm;                // [2][ATILE]
+  double* sB = dsm + 2 * ATILE;    // [2][BTILE]
+  __shared__ double s_col[BN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  const int wm = (warp / WN) * 32, wn = (warp % WN) * 32;
   const int g = lane >> 2, t = lane & 3;
 
-  // k range; a lower-triangular stored A restricts it (rows of op(A) in this tile: m0..m0+127)
+  // k range; a lower-triangular stored A restricts it (rows of op(A) in this tile: m0..m0+BM-1)
   int64_t kb = 0, ke = k;
   const int triA = (flags & GPK_GEMM_A_LOWER) ? 1 : 0;
   if (triA) {
     if (TA) kb = (m0 / DK) * DK;                // op(A)[i][kk] = S[kk][i], nonzero iff kk >= i
-    else ke = min(k, m0 + GB);                  // op(A)[i][kk] = S[i][kk], nonzero iff kk <= i
+    else ke = min(k, m0 + BM);                  // op(A)[i][kk] = S[i][kk], nonzero iff kk <= i
   }
 
   double acc[4][4][2];
@@ -98,46 +105,46 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[4], rb[4];
+  double ra[BM * DK / NT], rb[BN * DK / NT];
   const int nchunks = (int)((ke - kb + DK - 1) / DK);
   if (nchunks > 0) {
-    dload<!TA>(ra, A, lda, m0, m, kb, ke, tid, triA);
-    dload<TB>(rb, B, ldb, n0, n, kb, ke, tid, 0);
-    dstore<!TA>(ra, sA, tid);
-    dstore<TB>(rb, sB, tid);
+    dload<!TA, BM, NT>(ra, A, lda, m0, m, kb, ke, tid, triA);
+    dload<TB, BN, NT>(rb, B, ldb, n0, n, kb, ke, tid, 0);
+    dstore<!TA, BM, NT>(ra, sA, tid);
+    dstore<TB, BN, NT>(rb, sB, tid);
   }
   __syncthreads();
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
     if (c + 1 < nchunks) {
-      dload<!TA>(ra, A, lda, m0, m, kb + (int64_t)(c + 1) * DK, ke, tid, triA);
-      dload<TB>(rb, B, ldb, n0, n, kb + (int64_t)(c + 1) * DK, ke, tid, 0);
+      dload<!TA, BM, NT>(ra, A, lda, m0, m, kb + (int64_t)(c + 1) * DK, ke, tid, triA);
+      dload<TB, BN, NT>(rb, B, ldb, n0, n, kb + (int64_t)(c + 1) * DK, ke, tid, 0);
     }
-    const double* cA = sA + cur * DTILE;
-    const double* cB = sB + cur * DTILE;
+    const double* cA = sA + cur * ATILE;
+    const double* cB = sB + cur * BTILE;
 #pragma unroll
     for (int k4 = 0; k4 < DK; k4 += 4) {
       double af[4], bf[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        af[i] = !TA ? cA[(wm + i * 8 + g) * DS_K + k4 + t] : cA[(k4 + t) * DS_M + wm + i * 8 + g];
+        af[i] = !TA ? cA[(wm + i * 8 + g) * DS_K + k4 + t] : cA[(k4 + t) * (BM + 4) + wm + i * 8 + g];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        bf[j] = TB ? cB[(wn + j * 8 + g) * DS_K + k4 + t] : cB[(k4 + t) * DS_M + wn + j * 8 + g];
+        bf[j] = TB ? cB[(wn + j * 8 + g) * DS_K + k4 + t] : cB[(k4 + t) * (BN + 4) + wn + j * 8 + g];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     if (c + 1 < nchunks) {
-      dstore<!TA>(ra, sA + (cur ^ 1) * DTILE, tid);
-      dstore<TB>(rb, sB + (cur ^ 1) * DTILE, tid);
+      dstore<!TA, BM, NT>(ra, sA + (cur ^ 1) * ATILE, tid);
+      dstore<TB, BN, NT>(rb, sB + (cur ^ 1) * BTILE, tid);
     }
     __syncthreads();
   }
 
   if (flags & GPK_GEMM_COLSUMSQ) {
-    if (tid < GB) s_col[tid] = 0.0;
+    if (tid < BN) s_col[tid] = 0.0;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -157,7 +164,7 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
         if (g == 0) atomicAdd(&s_col[wn + j * 8 + 2 * t + h], s);
       }
     __syncthreads();
-    if (tid < GB && n0 + tid < n) atomicAdd(&C[n0 + tid], s_col[tid]);
+    if (tid < BN && n0 + tid < n) atomicAdd(&C[n0 + tid], s_col[tid]);
     return;
   }
 
@@ -183,12 +190,13 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
       }
     }
   }
-  if (head_flag && n0 == 0) {  // publish: this head tile is complete ([0] all head tiles, [1] diagonal tile)
+  if (head_flag && n0 < 128) {  // publish progress on the leading block column / the leading 128x128 block
     __syncthreads();
     if (tid == 0) {
       __threadfence();
       atomicAdd(head_flag, 1);
-      if (m0 == 0) atomicAdd(head_flag + 1, 1);
+      const int u = diag_units_tile(m0, n0, BM, BN, m, n);
+      if (u) atomicAdd(head_flag + 1, u);
     }
   }
 }
@@ -314,12 +322,13 @@ gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t l
       *dst = beta != T(0) ? v + beta * *dst : v;
     }
   }
-  if (head_flag && n0 == 0) {
+  if (head_flag && n0 < 128) {
     __syncthreads();
     if (tid == 0) {
       __threadfence();
       atomicAdd(head_flag, 1);
-      if (m0 == 0) atomicAdd(head_flag + 1, 1);
+      const int u = diag_units_tile(m0, n0, GB, GB, m, n);
+      if (u) atomicAdd(head_flag + 1, u);
     }
   }
 }
@@ -428,24 +437,53 @@ static int launch_simt(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t 
   return 0;
 }
 
-static int launch_dmma(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                       int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags,
-                       cudaStream_t st, int* hf) {
-  const size_t smem = 4 * DTILE * sizeof(double);  // 80 KB
+template <int BM, int BN>
+static int launch_dmma_shape(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                             const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags,
+                             cudaStream_t st, int* hf) {
+  constexpr int NT = (BM / 32) * (BN / 32) * 32;
+  constexpr int ATILE = BM * DS_K > DK * (BM + 4) ? BM * DS_K : DK * (BM + 4);
+  constexpr int BTILE = BN * DS_K > DK * (BN + 4) ? BN * DS_K : DK * (BN + 4);
+  const size_t smem = (size_t)(2 * ATILE + 2 * BTILE) * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-#define GO(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, 512, smem, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+  if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
+  GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
+#define GO(TA_, TB_) gemm_dmma_kernel<TA_, TB_, BM, BN><<<grid, NT, smem, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
   if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
   else if (ta && !tb) GO(true, false); else GO(true, true);
 #undef GO
   GPK_LAUNCH_OK();
   return 0;
+}
+
+static int launch_dmma(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                       int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags,
+                       cudaStream_t st, int* hf) {
+  // shape selection: 128x128 when there are enough tiles to fill the machine, otherwise narrower tiles.
+  // In-place contract: C aliasing A needs one tile across n (BN >= n), C aliasing B one tile across m.
+  const bool alias_a = (const void*)C == (const void*)A, alias_b = (const void*)C == (const void*)B;
+  const int64_t t128 = ((m + 127) / 128) * ((n + 127) / 128);
+#define SHAPE(BM_, BN_) return launch_dmma_shape<BM_, BN_>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf)
+  if (t128 >= 120 || (flags & GPK_GEMM_COLSUMSQ)) SHAPE(128, 128);
+  if (alias_b || (m <= 128 && !alias_a)) {          // short and wide: split the columns finer
+    if ((n + 63) / 64 >= 100) SHAPE(128, 64);
+    SHAPE(128, 32);
+  }
+  if (alias_a || n <= 128) {                        // tall and narrow: split the rows finer
+    if ((m + 63) / 64 >= 100) SHAPE(64, 128);
+    SHAPE(32, 128);
+  }
+  if (((m + 63) / 64) * ((n + 127) / 128) >= 100) SHAPE(64, 128);
+  SHAPE(32, 128);
+#undef SHAPE
 }
 
 template <typename T>
@@ -462,12 +500,12 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
     return gemm_tf32(transa, transb, m, n, k, (float)alpha, (const float*)A, lda, (const float*)B, ldb, (float)beta,
                      (float*)C, ldc, flags, st);
   ProfScope ps(PROF_GEMM, st);
+  if (sizeof(T) == 8 && !fp64_simt())
+    return launch_dmma(transa, transb, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
+                       (double)beta, (double*)C, ldc, flags, st, hf);
   dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB));
   if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
   GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
-  if (sizeof(T) == 8 && !fp64_simt())
-    return launch_dmma(transa, transb, grid, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
-                       (double)beta, (double*)C, ldc, flags, st, hf);
   return launch_simt<T>(transa, transb, grid, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf);
 }
 

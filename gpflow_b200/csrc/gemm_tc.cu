@@ -259,7 +259,8 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
         if (threadIdx.x == 64) {
           __threadfence();
           atomicAdd(head_flag, 1);
-          if (it.tm == 0) atomicAdd(head_flag + 1, 1);  // tiles of the next diagonal block
+          const int u = diag_units_tile(it.tm * TC_BM, it.tn * TC_BN, TC_BM, TC_BN, m, n);
+          if (u) atomicAdd(head_flag + 1, u);  // progress on the next diagonal block
         }
       }
     }

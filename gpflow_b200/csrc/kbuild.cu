@@ -458,10 +458,8 @@ __device__ __forceinline__ void stationary_value4(const double (&r2in)[4], doubl
     for (int q = 0; q < 4; ++q) x[q] = fmax(r2in[q], 1e-36);
 #pragma unroll
     for (int q = 0; q < 4; ++q) y[q] = (double)rsqrt_approx((float)x[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) e[q] = fma(-x[q] * y[q], y[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) y[q] = fma(0.5 * y[q], e[q], y[q]);
+    // y ~ x^-1/2 to 2^-22 (MUFU) -> one Newton step (2^-43) -> r = x*y and one Heron correction of r
+    // with the refined y: relative error ~2^-85 before rounding
 #pragma unroll
     for (int q = 0; q < 4; ++q) e[q] = fma(-x[q] * y[q], y[q], 1.0);
 #pragma unroll
@@ -521,7 +519,7 @@ __device__ __forceinline__ void stationary_value4(const double (&r2in)[4], doubl
 constexpr int KF_TS = KB_TILE + 1;  // transpose staging stride
 
 template <typename T, int TYPE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
                    const T* __restrict__ X2, int64_t N2, int64_t ldx2, T* __restrict__ K, int64_t ldk, int mode,
                    T diag_scalar, const T* __restrict__ diag_vec, int vec_ok) {

@@ -12,6 +12,10 @@
 // forward/back substitution blocks — is then a dense GEMM (gemm.cu / gemm_tc.cu) with K >= 128.
 // Rows below the square part (`rows > n`) ride along, so appending (Y-m)^T as extra rows yields
 // alpha^T = (L^-1 (Y-m))^T without a separate TRSV (logdensities.py:150).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace gpk {
@@ -395,23 +399,27 @@ static bool lookahead_enabled() {
   return v == 1;
 }
 
-static int lookahead_init(LookAhead& la, int* flag) {
-  static cudaStream_t side[16] = {nullptr};
-  static cudaEvent_t evs[16][3] = {{nullptr}};
+static int lookahead_init(LookAhead& la, int* flag, cudaStream_t st) {
+  // one side stream + event set per (device, caller stream): independent factorisations issued on
+  // different streams (e.g. one model per output) never share look-ahead state
+  struct Res { cudaStream_t side; cudaEvent_t ev[3]; };
+  static std::map<std::pair<int, cudaStream_t>, Res> pool;
+  static std::mutex mu;
   if (!lookahead_enabled() || !flag) return 0;
   int dev = 0;
   GPK_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return 0;
-  if (!side[dev]) {
-    GPK_CUDA_OK(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
-    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][0], cudaEventDisableTiming));
-    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][1], cudaEventDisableTiming));
-    GPK_CUDA_OK(cudaEventCreateWithFlags(&evs[dev][2], cudaEventDisableTiming));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = pool.find({dev, st});
+  if (it == pool.end()) {
+    Res r;
+    GPK_CUDA_OK(cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) GPK_CUDA_OK(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+    it = pool.emplace(std::make_pair(dev, st), r).first;
   }
-  la.side = side[dev];
-  la.ev_inputs = evs[dev][0];
-  la.ev_side = evs[dev][1];
-  la.ev_u = evs[dev][2];
+  la.side = it->second.side;
+  la.ev_inputs = it->second.ev[0];
+  la.ev_side = it->second.ev[1];
+  la.ev_u = it->second.ev[2];
   la.flag = flag;
   la.enabled = true;
   return 0;
@@ -426,7 +434,7 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
   if (la.enabled) {
     GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 2 * sizeof(int), st));
     opts.head_flag = la.flag;
-    la.target = use_tc ? (n > 64 ? 2 : 1) : 1;  // tiles covering the next 128x128 diagonal block
+    la.target = diag_units_total(m, n);  // 32x32 units of the next 128x128 diagonal block
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
     la.pending = true;
   }
@@ -490,7 +498,7 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   LookAhead la;
   // the look-ahead counter lives in the last 256 bytes of the dinv area's alignment slack (see potrf_ws_bytes)
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(dinv) + (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(T));
-  if (n > NB) GPK_TRY(lookahead_init(la, flag));
+  if (n > NB) GPK_TRY(lookahead_init(la, flag, st));
   return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, la, st);
 }
 
