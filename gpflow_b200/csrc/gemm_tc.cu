@@ -130,7 +130,7 @@ struct TcTileIter {  // identical enumeration in every warp role
   }
 };
 
-template <int S>
+template <int S, bool TS>
 __global__ void __launch_bounds__(192, 1)
 syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
                int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err, int* head_flag) {
@@ -202,13 +202,28 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
         const uint64_t ad0 = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
         const uint64_t bd0 = ad0 + ((TC_MAXS * TC_ATILE) >> 4);
         if (elect_one()) {
+          if (TS) {
+            // A digit planes -> TMEM (columns S*64 .. S*64 + 8S): every A plane is then read from shared
+            // memory once per k-step instead of once per MMA (S-s times); tcgen05.cp and tcgen05.mma execute
+            // in issue order, so the copy for this k-step queues behind the previous step's MMAs.
+            const uint32_t a_tm = tmem_base + (uint32_t)S * TC_BN;
 #pragma unroll
-          for (int s = 0; s < S; ++s)
+            for (int s = 0; s < S; ++s) tc_cp_128x256b(a_tm + s * 8, ad0 + (uint64_t)(s * (TC_ATILE >> 4)));
 #pragma unroll
-            for (int t = 0; t + s < S; ++t)
-              tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
-                        bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
-          tc_commit(empty0 + 8 * st);  // frees the stage once these MMAs have read it
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+              for (int t = 0; t + s < S; ++t)
+                tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
+                             TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+              for (int t = 0; t + s < S; ++t)
+                tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
+                          bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+          }
+          tc_commit(empty0 + 8 * st);  // frees the stage once these copies / MMAs have read it
         }
         __syncwarp();
         if (++st == TC_STAGES) { st = 0; ph ^= 1; }
@@ -333,9 +348,11 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
   static bool attr = false;
   if (!attr) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   // number of tiles
@@ -346,12 +363,13 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   if (ntiles < grid) grid = (int)ntiles;
   if (grid < 1) return 0;
   ProfScope ps(PROF_GEMM, st);
-  if (S == 6)
-    syrk_i8_kernel<6><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
-  else if (S == 7)
-    syrk_i8_kernel<7><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
-  else
-    syrk_i8_kernel<8><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf);
+  // A planes through TMEM (tcgen05.cp + TS-form MMA) by default; GPK_TC_A_TMEM=0 selects the SS form
+  static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return !(e && e[0] == '0'); }();
+#define GPK_TC_GO(S_, TS_) syrk_i8_kernel<S_, TS_><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf)
+  if (S == 6) { if (ts) GPK_TC_GO(6, true); else GPK_TC_GO(6, false); }
+  else if (S == 7) { if (ts) GPK_TC_GO(7, true); else GPK_TC_GO(7, false); }
+  else GPK_TC_GO(8, false);  // S = 8 leaves no TMEM columns for the A planes
+#undef GPK_TC_GO
   GPK_LAUNCH_OK();
   return 0;
 }
