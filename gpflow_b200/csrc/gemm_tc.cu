@@ -95,12 +95,14 @@ constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
                               ((uint32_t)(TC_BM >> 4) << 24);
 
 struct TcTileIter {  // identical enumeration in every warp role
-  // Order: pass 0 = the "head" tiles (first 128 columns: tn < 2) of every row tile, pass 1 = the rest,
-  // so the next diagonal block's inputs are complete early (look-ahead, see potrf.cu).
+  // Work unit = CL horizontally adjacent tiles (tm, tnb .. tnb+CL-1), one per CTA of a cluster, so the
+  // cluster shares the A tile (multicast).  Order: pass 0 = the "head" units (first 128 columns) of every
+  // row tile, pass 1 = the rest: the next diagonal block's inputs are complete early (look-ahead).
   int64_t ntm, ntn;
-  int lower, pass;
-  int64_t tm, tn, idx;
-  __device__ TcTileIter(int64_t m, int64_t n, int lower_) : lower(lower_), pass(0), tm(0), tn(-1), idx(-1) {
+  int lower, pass, cl, rank;
+  int64_t tm, tnb, tn, idx;
+  __device__ TcTileIter(int64_t m, int64_t n, int lower_, int cl_, int rank_)
+      : lower(lower_), pass(0), cl(cl_), rank(rank_), tm(0), tnb(-cl_), tn(0), idx(-1) {
     ntm = (m + TC_BM - 1) / TC_BM;
     ntn = (n + TC_BN - 1) / TC_BN;
   }
@@ -109,28 +111,32 @@ struct TcTileIter {  // identical enumeration in every warp role
     return lower ? (lim < ntn ? lim : ntn) : ntn;
   }
   __device__ bool is_head() const { return pass == 0; }
-  // advances to this CTA's next tile; false when exhausted
+  // tile index used for LOADING B (clamped: the odd CTA of a last, half-empty unit loads valid memory and
+  // its epilogue writes nothing because its columns are >= n)
+  __device__ int64_t tn_load() const { return tn < ntn ? tn : ntn - 1; }
+  // advances to this cluster's next unit; false when exhausted
   __device__ bool next() {
+    const int64_t nunits_grid = gridDim.x / cl, my = blockIdx.x / cl;
     for (;;) {
-      ++tn;
+      tnb += cl;
       for (;;) {
         if (pass == 0) {
           const int64_t lim = ncols(tm) < 2 ? ncols(tm) : 2;
-          if (tm < ntm && tn >= lim) { ++tm; tn = 0; continue; }
-          if (tm >= ntm) { pass = 1; tm = 0; tn = 2; continue; }
+          if (tm < ntm && tnb >= lim) { ++tm; tnb = 0; continue; }
+          if (tm >= ntm) { pass = 1; tm = 0; tnb = 2; continue; }
         } else {
-          if (tm < ntm && tn >= ncols(tm)) { ++tm; tn = 2; continue; }
+          if (tm < ntm && tnb >= ncols(tm)) { ++tm; tnb = 2; continue; }
           if (tm >= ntm) return false;
         }
         break;
       }
       ++idx;
-      if (idx % gridDim.x == blockIdx.x) return true;
+      if (idx % nunits_grid == my) { tn = tnb + rank; return true; }
     }
   }
 };
 
-template <int S, bool TS>
+template <int S, bool TS, int CL>
 __global__ void __launch_bounds__(192, 1)
 syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
                int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err, int* head_flag) {
@@ -147,7 +153,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, CL);  // every CTA of the cluster releases a stage (A is multicast into all)
     }
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
@@ -161,16 +167,20 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers initialised before any multicast copy / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     // ===== producer (whole warp runs the loop; one elected lane issues the copies) =====
-    TcTileIter it(m, n, lower);
+    TcTileIter it(m, n, lower, CL, rank);
     uint32_t st = 0, ph = 0;
     while (it.next()) {
       const int8_t* a_src = tiles + (size_t)it.tm * KB * S * TC_ATILE;
-      const int8_t* b_src = tiles + (size_t)(it.tn >> 1) * KB * S * TC_ATILE + (it.tn & 1) * TC_BTILE;
+      const int64_t tl = it.tn_load();
+      const int8_t* b_src = tiles + (size_t)(tl >> 1) * KB * S * TC_ATILE + (tl & 1) * TC_BTILE;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(empty0 + 8 * st, ph ^ 1, err, 101);
         if (elect_one()) {
@@ -178,7 +188,16 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
           const uint32_t sb = sa + TC_MAXS * TC_ATILE;
-          bulk_g2s(sa, a_src + (size_t)kb * S * TC_ATILE, (uint32_t)S * TC_ATILE, fb);
+          if (CL == 1) {
+            bulk_g2s(sa, a_src + (size_t)kb * S * TC_ATILE, (uint32_t)S * TC_ATILE, fb);
+          } else {
+            // each CTA fetches 1/CL of every A plane (64 of the 128 rows) and multicasts it to the cluster
+            constexpr uint32_t part = TC_ATILE / CL;
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2)
+              bulk_g2s_mc(sa + s2 * TC_ATILE + rank * part, a_src + ((size_t)kb * S + s2) * TC_ATILE + rank * part, part, fb,
+                          cl_mask);
+          }
 #pragma unroll
           for (int t = 0; t < S; ++t)
             bulk_g2s(sb + t * TC_BTILE, b_src + ((size_t)kb * S + t) * TC_ATILE, TC_BTILE, fb);
@@ -189,7 +208,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
     }
   } else if (warp == 1) {
     // ===== MMA issuer (uniform control flow, one elected lane issues) =====
-    TcTileIter it(m, n, lower);
+    TcTileIter it(m, n, lower, CL, rank);
     uint32_t st = 0, ph = 0, tph = 0;
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
     while (it.next()) {
@@ -223,7 +242,8 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
                 tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
                           bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
           }
-          tc_commit(empty0 + 8 * st);  // frees the stage once these copies / MMAs have read it
+          // frees the stage (in every CTA of the cluster) once these copies / MMAs have read it
+          if (CL == 1) tc_commit(empty0 + 8 * st); else tc_commit_mc(empty0 + 8 * st, cl_mask);
         }
         __syncwarp();
         if (++st == TC_STAGES) { st = 0; ph ^= 1; }
@@ -235,7 +255,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
   } else {
     // ===== epilogue (4 warps = 128 TMEM lanes) =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    TcTileIter it(m, n, lower);
+    TcTileIter it(m, n, lower, CL, rank);
     uint32_t tph = 0;
     while (it.next()) {
       mbar_wait(tfull, tph, err, 104);
@@ -283,6 +303,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
@@ -346,32 +367,50 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
     GPK_LAUNCH_OK();
   }
   const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
-  static bool attr = false;
-  if (!attr) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GPK_CUDA_OK(cudaFuncSetAttribute(syrk_i8_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  // number of tiles
+  // A planes through TMEM (tcgen05.cp + TS-form MMA) by default; GPK_TC_A_TMEM=0 selects the SS form.
+  // Clusters of 2 CTAs multicast the shared A tile (the kernel is L2->SM bandwidth bound); GPK_TC_CLUSTER=1 disables.
+  static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return !(e && e[0] == '0'); }();
+  static const int cl = []() { const char* e = getenv("GPK_TC_CLUSTER"); return (e && e[0] == '1') ? 1 : 2; }();
+  // number of work units (CL adjacent tiles)
   const int64_t ntm = (m + TC_BM - 1) / TC_BM, ntn = (n + TC_BN - 1) / TC_BN;
-  int64_t ntiles = 0;
-  for (int64_t t = 0; t < ntm; ++t) ntiles += lower ? (2 * t + 2 < ntn ? 2 * t + 2 : ntn) : ntn;
+  int64_t nunits = 0;
+  for (int64_t t = 0; t < ntm; ++t) {
+    const int64_t nc = lower ? (2 * t + 2 < ntn ? 2 * t + 2 : ntn) : ntn;
+    nunits += (nc + cl - 1) / cl;
+  }
   int grid = tc_num_sms() - (hf ? 1 : 0);  // look-ahead: leave one SM for the concurrent leaf kernel
-  if (ntiles < grid) grid = (int)ntiles;
+  grid = grid / cl * cl;
+  if (nunits * cl < grid) grid = (int)(nunits * cl);
   if (grid < 1) return 0;
   ProfScope ps(PROF_GEMM, st);
-  // A planes through TMEM (tcgen05.cp + TS-form MMA) by default; GPK_TC_A_TMEM=0 selects the SS form
-  static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return !(e && e[0] == '0'); }();
-#define GPK_TC_GO(S_, TS_) syrk_i8_kernel<S_, TS_><<<grid, 192, smem, st>>>(tiles, rowscale, C, ldc, m, n, (int)(K / TC_KB), lower, err, hf)
-  if (S == 6) { if (ts) GPK_TC_GO(6, true); else GPK_TC_GO(6, false); }
-  else if (S == 7) { if (ts) GPK_TC_GO(7, true); else GPK_TC_GO(7, false); }
-  else GPK_TC_GO(8, false);  // S = 8 leaves no TMEM columns for the A planes
-#undef GPK_TC_GO
-  GPK_LAUNCH_OK();
-  return 0;
+  const int KBn = (int)(K / TC_KB);
+  auto launch = [&](auto kern) -> int {
+    static_cast<void>(0);
+    GPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const int8_t*)tiles, (const double*)rowscale, C, ldc, m, n, KBn, lower, err, hf));
+    count_launch();
+    return 0;
+  };
+  if (cl == 2) {
+    if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 2>) : launch(syrk_i8_kernel<6, false, 2>);
+    if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 2>) : launch(syrk_i8_kernel<7, false, 2>);
+    return launch(syrk_i8_kernel<8, false, 2>);
+  }
+  if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 1>) : launch(syrk_i8_kernel<6, false, 1>);
+  if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 1>) : launch(syrk_i8_kernel<7, false, 1>);
+  return launch(syrk_i8_kernel<8, false, 1>);
 }
 
 }  // namespace gpk
