@@ -84,7 +84,8 @@ SIGNATURES = {
                               c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgpk.so")
+# GPFLOW_B200_LIB selects another build of the same ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("GPFLOW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgpk.so")
 _lib: Optional[ctypes.CDLL] = None
 
 

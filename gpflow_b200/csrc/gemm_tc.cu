@@ -114,6 +114,9 @@ struct TcTileIter {  // identical enumeration in every warp role
   // tile index used for LOADING B (clamped: the odd CTA of a last, half-empty unit loads valid memory and
   // its epilogue writes nothing because its columns are >= n)
   __device__ int64_t tn_load() const { return tn < ntn ? tn : ntn - 1; }
+  // false for the padding tiles of a unit that sticks out of the (lower-triangular) tile set: computed, not stored
+  __device__ bool valid() const { return tn < ncols(tm); }
+  __device__ int64_t head_w() const { return cl > 2 ? cl : 2; }
   // advances to this cluster's next unit; false when exhausted
   __device__ bool next() {
     const int64_t nunits_grid = gridDim.x / cl, my = blockIdx.x / cl;
@@ -121,11 +124,11 @@ struct TcTileIter {  // identical enumeration in every warp role
       tnb += cl;
       for (;;) {
         if (pass == 0) {
-          const int64_t lim = ncols(tm) < 2 ? ncols(tm) : 2;
+          const int64_t lim = ncols(tm) < head_w() ? ncols(tm) : head_w();
           if (tm < ntm && tnb >= lim) { ++tm; tnb = 0; continue; }
-          if (tm >= ntm) { pass = 1; tm = 0; tnb = 2; continue; }
+          if (tm >= ntm) { pass = 1; tm = 0; tnb = head_w(); continue; }
         } else {
-          if (tm < ntm && tnb >= ncols(tm)) { ++tm; tnb = 2; continue; }
+          if (tm < ntm && tnb >= ncols(tm)) { ++tm; tnb = head_w(); continue; }
           if (tm >= ntm) return false;
         }
         break;
@@ -277,7 +280,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
           w *= 0.0078125;  // 2^-7
         }
         const int64_t col0 = it.tn * TC_BN + half * 32;
-        if (row < m) {
+        if (row < m && it.valid()) {
           double* crow = C + row * ldc + col0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -370,7 +373,10 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   // A planes through TMEM (tcgen05.cp + TS-form MMA) by default; GPK_TC_A_TMEM=0 selects the SS form.
   // Clusters of 2 CTAs multicast the shared A tile (the kernel is L2->SM bandwidth bound); GPK_TC_CLUSTER=1 disables.
   static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return !(e && e[0] == '0'); }();
-  static const int cl = []() { const char* e = getenv("GPK_TC_CLUSTER"); return (e && e[0] == '1') ? 1 : 2; }();
+  static const int cl = []() {
+    const char* e = getenv("GPK_TC_CLUSTER");
+    return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2;
+  }();
   // number of work units (CL adjacent tiles)
   const int64_t ntm = (m + TC_BM - 1) / TC_BM, ntn = (n + TC_BN - 1) / TC_BN;
   int64_t nunits = 0;
@@ -403,6 +409,11 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
     count_launch();
     return 0;
   };
+  if (cl == 4) {
+    if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 4>) : launch(syrk_i8_kernel<6, false, 4>);
+    if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 4>) : launch(syrk_i8_kernel<7, false, 4>);
+    return launch(syrk_i8_kernel<8, false, 4>);
+  }
   if (cl == 2) {
     if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 2>) : launch(syrk_i8_kernel<6, false, 2>);
     if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 2>) : launch(syrk_i8_kernel<7, false, 2>);

@@ -15,6 +15,7 @@
 
 #include <vector>
 
+#include <type_traits>
 #include "common.cuh"
 
 namespace gpk {
@@ -381,123 +382,93 @@ __constant__ double c_exp2_tab[64];
 static double h_exp2_tab[64];
 static bool h_exp2_tab_ready = false;
 
-__device__ __forceinline__ double fast_exp_neg(double x, const double* __restrict__ tab) {  // x <= 0, tab in SHARED memory
-  if (x < -708.0) return 0.0;
-  const double t = x * 92.33248261689366;  // 64 / ln 2
-  const double sh = t + 6755399441055744.0;              // 1.5 * 2^52: round-to-nearest integer in the low bits
-  const double kd = sh - 6755399441055744.0;
-  const int k = __double2loint(sh);
-  double r = fma(kd, -0.01083042468962958, x);           // ln2/64 hi (low 22 mantissa bits zero: kd*hi exact)
-  r = fma(kd, -6.619564634077006e-12, r);                // ln2/64 lo
-  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-  p = fma(p, r, 1.6666666666666666e-01);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int j = k & 63, n = k >> 6;                      // k = 64 n + j, floor semantics for negative k
-  const double two_n = __longlong_as_double((long long)(n + 1023) << 52);
-  return tab[j] * p * two_n;  // lanes hit different entries: shared memory, never __constant__
+// The fast path works on x = c * r2 (c folded into the per-dimension weights on the host together with the
+// 1/lengthscale^2 scale): RBF c = 1/2 (k = v exp(-x)), Matern12 c = 1 (u = sqrt x, k = v exp(-u)),
+// Exponential c = 1/4, Matern32 c = 3 (k = v (1 + u) exp(-u)), Matern52 c = 5 (k = v (1 + u + x/3) exp(-u)).
+// The reference's clip of r2 at 1e-36 (stationaries.py:130-136) becomes a clip of x at c * 1e-36.
+template <int TYPE> __host__ __device__ constexpr double kf_fold() {
+  return TYPE == GPK_K_RBF ? 0.5 : TYPE == GPK_K_MATERN32 ? 3.0 : TYPE == GPK_K_MATERN52 ? 5.0
+       : TYPE == GPK_K_EXPONENTIAL ? 0.25 : 1.0;
 }
-__device__ __forceinline__ double fast_sqrt_pos(double x) {  // x >= 1e-36
-  double y = (double)__frsqrt_rn((float)x);  // MUFU.RSQ seed
-  double e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  double s = x * y;
-  return fma(0.5 * y, fma(-s, s, x), s);
+template <int TYPE> __host__ __device__ constexpr bool kf_const_pre() {  // prefactor is just the variance
+  return TYPE == GPK_K_RBF || TYPE == GPK_K_MATERN12 || TYPE == GPK_K_EXPONENTIAL;
 }
 
-template <typename T> struct FastMath;
-template <> struct FastMath<double> {
-  static __device__ __forceinline__ double exp_neg(double x, const double* tab) { return fast_exp_neg(x, tab); }
-  static __device__ __forceinline__ double sqrt_pos(double x) { return fast_sqrt_pos(x); }
-};
-template <> struct FastMath<float> {
-  static __device__ __forceinline__ float exp_neg(float x, const double*) { return __expf(x); }
-  static __device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
-};
-
-template <typename T, int TYPE>
-__device__ __forceinline__ T stationary_value(T r2, T var, const double* tab) {
-  using F = FastMath<T>;
-  if (TYPE == GPK_K_RBF) return var * F::exp_neg(fmin(T(-0.5) * r2, T(0)), tab);
-  const T r2c = fmax(r2, T(1e-36));
-  const T r = F::sqrt_pos(r2c);
-  if (TYPE == GPK_K_MATERN52) {
-    const T s5 = T(2.23606797749978969641);
-    return var * fma(T(5.0 / 3.0), r2c, fma(s5, r, T(1))) * F::exp_neg(-s5 * r, tab);
-  }
-  if (TYPE == GPK_K_MATERN32) {
-    const T s3 = T(1.73205080756887729353);
-    return var * fma(s3, r, T(1)) * F::exp_neg(-s3 * r, tab);
-  }
-  if (TYPE == GPK_K_MATERN12) return var * F::exp_neg(-r, tab);
-  return var * F::exp_neg(T(-0.5) * r, tab);  // Exponential
+// fp32 value (generic float path): plain library math, the SFU exp is accurate enough for fp32
+template <int TYPE>
+__device__ __forceinline__ float stationary_value_f32(float x, float var) {
+  if (TYPE == GPK_K_RBF) return var * __expf(-fmaxf(x, 0.0f));
+  const float xc = fmaxf(x, (float)(kf_fold<TYPE>() * 1e-36));
+  const float u = sqrtf(xc);
+  if (TYPE == GPK_K_MATERN52) return fmaf(var * (1.0f / 3.0f), xc, fmaf(var, u, var)) * __expf(-u);
+  if (TYPE == GPK_K_MATERN32) return fmaf(var, u, var) * __expf(-u);
+  return var * __expf(-u);
 }
 
-// Four elements at a time, stage by stage: every arithmetic step is issued for the four independent
-// elements back to back, so the long dependent chains (sqrt: ~8, exp: ~12 fp64 ops) overlap instead of
-// each waiting out the fp64 latency alone.
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+// Four fp64 elements at a time, stage by stage: every arithmetic step is issued for the four independent
+// elements back to back, so the dependent chains (sqrt: 6, exp: 11 fp64 ops) overlap instead of each
+// waiting out the fp64 latency alone.  fp64-pipe budget per element (Matern52): 2 (x) + 6 (sqrt) + 2 (pre)
+// + 11 (exp) = 21 besides the D-term dot product; clamps, range checks and the 2^n scaling are integer ops.
+//   tab: 2^(j/64) in SHARED memory (lanes hit different entries), pre-multiplied by the variance when the
+//   prefactor is constant.  var_ok: variance >= 2^-100, so adding n to the exponent field cannot underflow
+//   while n >= -900 (the slow path handles the rest, including exp underflow to 0 below -708).
 template <int TYPE>
-__device__ __forceinline__ void stationary_value4(const double (&r2in)[4], double var, const double* __restrict__ tab,
-                                                  double (&out)[4]) {
-  double arg[4], pre[4];
+__device__ __forceinline__ void stationary_value4(const double (&xin)[4], double var, double var3, bool var_ok,
+                                                  const double* __restrict__ tab, double (&out)[4]) {
+  double u[4], pre[4];
   if (TYPE == GPK_K_RBF) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { arg[q] = fmin(-0.5 * r2in[q], 0.0); pre[q] = var; }
+    for (int q = 0; q < 4; ++q) u[q] = __double2hiint(xin[q]) < 0 ? 0.0 : xin[q];  // max(x, 0) on the integer pipe
   } else {
-    double x[4], y[4], e[4], r[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) x[q] = fmax(r2in[q], 1e-36);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) y[q] = (double)rsqrt_approx((float)x[q]);
-    // y ~ x^-1/2 to 2^-22 (MUFU) -> one Newton step (2^-43) -> r = x*y and one Heron correction of r
-    // with the refined y: relative error ~2^-85 before rounding
-#pragma unroll
-    for (int q = 0; q < 4; ++q) e[q] = fma(-x[q] * y[q], y[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) y[q] = fma(0.5 * y[q], e[q], y[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r[q] = x[q] * y[q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r[q] = fma(0.5 * y[q], fma(-r[q], r[q], x[q]), r[q]);
+    constexpr double clampv = kf_fold<TYPE>() * 1e-36;
+    double x[4], g[4], h[4], r[4], d[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (TYPE == GPK_K_MATERN52) {
-        const double s5 = 2.23606797749978969641;
-        pre[q] = var * fma(5.0 / 3.0, x[q], fma(s5, r[q], 1.0));
-        arg[q] = -s5 * r[q];
-      } else if (TYPE == GPK_K_MATERN32) {
-        const double s3 = 1.73205080756887729353;
-        pre[q] = var * fma(s3, r[q], 1.0);
-        arg[q] = -s3 * r[q];
-      } else if (TYPE == GPK_K_MATERN12) {
-        pre[q] = var;
-        arg[q] = -r[q];
-      } else {
-        pre[q] = var;
-        arg[q] = -0.5 * r[q];
-      }
+      // x < clamp (or negative) by a signed compare of the high words: equal high words differ by < 2^-20 relative
+      const int hi_c = (int)((unsigned long long)__double_as_longlong(clampv) >> 32);
+      x[q] = __double2hiint(xin[q]) < hi_c ? clampv : xin[q];
+    }
+    // y0 ~ x^-1/2 to 2^-22 (MUFU); g = x y0 ~ sqrt x, h = y0/2; one coupled Newton step on g (2^-43), then a
+    // Heron correction with the unrefined h: relative error 1.5 e0^3 ~ 2^-64 before rounding
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = (double)rsqrt_approx((float)x[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = x[q] * h[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = 0.5 * h[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = fma(-g[q], h[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = fma(g[q], r[q], g[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] = fma(-g[q], g[q], x[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = fma(h[q], d[q], g[q]);
+    if (TYPE == GPK_K_MATERN52) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[q] = fma(var3, x[q], fma(var, u[q], var));
+    } else if (TYPE == GPK_K_MATERN32) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[q] = fma(var, u[q], var);
     }
   }
-  // exp(arg), arg <= 0
+  // exp(-u), u >= 0
   double sh[4], kd[4], rr[4], p[4];
   int k[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) sh[q] = fma(arg[q], 92.33248261689366, 6755399441055744.0);
+  for (int q = 0; q < 4; ++q) sh[q] = fma(u[q], -92.33248261689366, 6755399441055744.0);  // round(-u 64/ln2) in the low bits
 #pragma unroll
   for (int q = 0; q < 4; ++q) { kd[q] = sh[q] - 6755399441055744.0; k[q] = __double2loint(sh[q]); }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -0.01083042468962958, arg[q]);
+  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -0.01083042468962958, -u[q]);   // ln2/64 hi (kd * hi exact)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -6.619564634077006e-12, rr[q]);
+  for (int q = 0; q < 4; ++q) rr[q] = fma(kd[q], -6.619564634077006e-12, rr[q]);  // ln2/64 lo
 #pragma unroll
   for (int q = 0; q < 4; ++q) p[q] = fma(rr[q], 8.3333333333333332e-03, 4.1666666666666664e-02);
 #pragma unroll
@@ -508,175 +479,266 @@ __device__ __forceinline__ void stationary_value4(const double (&r2in)[4], doubl
   for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 1.0);
 #pragma unroll
   for (int q = 0; q < 4; ++q) p[q] = fma(p[q], rr[q], 1.0);
+  double w[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const double two_n = __longlong_as_double((long long)((k[q] >> 6) + 1023) << 52);
-    const double v = pre[q] * tab[k[q] & 63] * p[q] * two_n;
-    out[q] = arg[q] < -708.0 ? 0.0 : v;
+    const double t = tab[k[q] & 63];
+    w[q] = (kf_const_pre<TYPE>() ? t : pre[q] * t) * p[q];
+  }
+  const int kmin = min(min(k[0], k[1]), min(k[2], k[3]));
+  if (var_ok && kmin >= -57600) {  // 2^n by an integer add on the exponent field (n >= -900, w >= 2^-101)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      out[q] = __hiloint2double(__double2hiint(w[q]) + ((k[q] >> 6) << 20), __double2loint(w[q]));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = max(k[q] >> 6, -1022);
+      const double two_n = __longlong_as_double((long long)(n + 1023) << 52);
+      out[q] = u[q] > 708.0 ? 0.0 : w[q] * two_n;
+    }
   }
 }
 
-constexpr int KF_TS = KB_TILE + 1;  // transpose staging stride
+#ifndef KF_VARIANT
+#define KF_VARIANT 0  // experiment switches (scripts/kb_variants.sh): 1 no stores, 2 no dots, 4 no evaluation
+#endif
+constexpr int KF_KC = 8;             // dims staged per chunk (fast path)
+constexpr int KF_LD = KB_TILE + 4;   // shared row stride of a staged dim: 16-byte aligned rows, 2-way store conflicts
 
-template <typename T, int TYPE>
-__global__ void __launch_bounds__(256, 3)
+// Persistent CTAs over the needed tiles (lower-triangle tiles of a symmetric K).  Per (tile, chunk of 8 dims)
+// the operand rows are fetched into REGISTERS one step ahead (the global-load latency overlaps the previous
+// step's arithmetic), scaled by the folded weights and staged transposed in shared memory.  Thread (tx,ty) of
+// a 16x16 grid owns a 4x4 micro-tile made of 2x2 blocks 32 apart (rows {2ty, 2ty+1, 32+2ty, 33+2ty}, columns
+// likewise with tx), warps are 8(tx) x 4(ty): every 16-byte store instruction of a warp then writes whole
+// 32-byte sectors -- 128-byte row runs for the direct tile, 64-byte runs for the MIRRORED tile of GPK_FULL,
+// which is written straight from registers (K[j][i] = K[i][j] is a copy, so K is bit-symmetric).
+template <typename T, int TYPE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 kbuild_fast_kernel(const __grid_constant__ KProg prog, const T* __restrict__ X, int64_t N, int64_t ldx,
                    const T* __restrict__ X2, int64_t N2, int64_t ldx2, T* __restrict__ K, int64_t ldk, int mode,
-                   T diag_scalar, const T* __restrict__ diag_vec, int vec_ok) {
-  // mode: 0 rectangular (2-D tile index from the 1-D grid), 1 symmetric lower-only, 2 symmetric full (mirror)
-  extern __shared__ __align__(16) unsigned char kf_smem[];
-  T* sA = reinterpret_cast<T*>(kf_smem);            // [KB_KC][KB_TILE]
-  T* sB = sA + KB_KC * KB_TILE;                     // [KB_KC][KB_TILE]
-  T* sNa = sB + KB_KC * KB_TILE;                    // [KB_TILE]
-  T* sNb = sNa + KB_TILE;                           // [KB_TILE]
-  T* sT = sNb + KB_TILE;                            // [KB_TILE][KF_TS] transpose staging (mode 2)
+                   T diag_scalar, const T* __restrict__ diag_vec, int vec_ok, int64_t ntiles) {
+  // mode: 0 rectangular, 1 symmetric lower-only, 2 symmetric full (mirror)
+  __shared__ __align__(16) T sA[2 * KF_KC * KF_LD];  // double-buffered staged operands [buf][dim][row]
+  __shared__ __align__(16) T sB[2 * KF_KC * KF_LD];
+  __shared__ T sNa[2 * KB_TILE], sNb[2 * KB_TILE];    // squared row norms of the staged rows
   __shared__ double s_tab[64];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  if (tid < 64) s_tab[tid] = c_exp2_tab[tid];
-  int64_t by, bx;
-  if (mode == 0) {
-    const int64_t ntx = (N2 + KB_TILE - 1) / KB_TILE;
-    by = blockIdx.x / ntx;
-    bx = blockIdx.x % ntx;
-  } else {  // lower-triangle tile enumeration: t = by (by + 1) / 2 + bx, bx <= by
-    const int64_t t = blockIdx.x;
-    by = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (by * (by + 1) / 2 > t) --by;
-    while ((by + 1) * (by + 2) / 2 <= t) ++by;
-    bx = t - by * (by + 1) / 2;
-  }
-  const int64_t row0 = by * KB_TILE, col0 = bx * KB_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = (lane & 7) + 8 * (warp & 1), ty = (lane >> 3) + 4 * (warp >> 1);
+  auto rowi = [&](int r) { return ((r >> 1) << 5) + ty * 2 + (r & 1); };  // tile row of micro-tile row r
+  auto coli = [&](int c) { return ((c >> 1) << 5) + tx * 2 + (c & 1); };  // tile column of micro-tile column c
+  const T var = T(prog.l_var[0]);
+  if (tid < 64) s_tab[tid] = kf_const_pre<TYPE>() ? c_exp2_tab[tid] * (double)var : c_exp2_tab[tid];
+  // prog.w carries sqrt(c / lengthscale^2) (kf_fold), so the norm expansion yields x = c r2 directly
+  const double var3 = (double)var * (1.0 / 3.0);
+  const bool var_ok = (double)var >= 7.888609052210118e-31;  // 2^-100
   const bool sym = mode != 0;
   const T* Xb = sym ? X : X2;
   const int64_t ldb = sym ? ldx : ldx2;
-
-  T dots[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) dots[r][c] = T(0);
-  if (tid < KB_TILE) { sNa[tid] = T(0); sNb[tid] = T(0); }
   const int nd = prog.g_ndims[0];
-  for (int d0 = 0; d0 < nd; d0 += KB_KC) {
-    const int kc = min(KB_KC, nd - d0);
-    __syncthreads();
-    for (int e = tid; e < kc * KB_TILE; e += 256) {
-      const int d = e % kc, r = e / kc;
-      const int col = prog.dims[d0 + d];
-      const int64_t gr = row0 + r, gc = col0 + r;
-      const T a = gr < N ? X[gr * ldx + col] : T(0);
-      const T b = gc < N2 ? Xb[gc * ldb + col] : T(0);
-      const T wv = T(prog.w[d0 + d]);   // 1 or 1/lengthscale_d, applied to both sides
-      sA[d * KB_TILE + r] = a * wv;
-      sB[d * KB_TILE + r] = b * wv;
+  const int nchunks = (nd + KF_KC - 1) / KF_KC;
+  const int64_t ntx = (N2 + KB_TILE - 1) / KB_TILE;
+
+  auto decode = [&](int t, int& by, int& bx) {  // tile counts fit 31 bits (checked on the host)
+    if (mode == 0) {
+      by = t / (int)ntx;
+      bx = t - by * (int)ntx;
+    } else {  // lower-triangle tile enumeration: t = by (by + 1) / 2 + bx, bx <= by
+      by = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // fp32 estimate, exact after the fix-up loops
+      while ((long long)by * (by + 1) / 2 > t) --by;
+      while ((long long)(by + 1) * (by + 2) / 2 <= t) ++by;
+      bx = t - (int)((long long)by * (by + 1) / 2);
     }
-    __syncthreads();
-    if (tid < 2 * KB_TILE) {  // squared norms of the staged rows / columns, identical expression
-      const int r = tid & (KB_TILE - 1);
-      const T* src = tid < KB_TILE ? sA : sB;
-      T acc = T(0);
-      for (int d = 0; d < kc; ++d) { const T v = src[d * KB_TILE + r]; acc = fma(v, v, acc); }
-      if (tid < KB_TILE) sNa[r] += acc; else sNb[r] += acc;
+  };
+  // Staging: this thread fetches rows sr0 and sr0 + 32 of both operands, dim sd of a chunk, one step ahead into
+  // registers, scales them and later writes them transposed into the step's shared buffer.  The squared row norms
+  // are reduced across the 8 lanes that hold one row (xor butterfly: every lane gets the same bits, and a row
+  // staged as the A side or as the B side sums in the same order, so K stays bit-symmetric).
+  const int sd = tid & 7, sr0 = tid >> 3;
+  T pa[2], pb[2];          // fetched (scaled) operands of the step after next
+  T qa[2] = {T(0), T(0)}, qb[2] = {T(0), T(0)};  // running squared norms of the rows this thread stages
+  auto fetch = [&](int by, int bx, int ch) {
+    const int d = ch * KF_KC + sd;
+    const bool dok = d < nd;
+    const int col = dok ? prog.dims[d] : 0;
+    const T wv = dok ? T(prog.w[d]) : T(0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t gr = (int64_t)by * KB_TILE + sr0 + 32 * i, gc = (int64_t)bx * KB_TILE + sr0 + 32 * i;
+      pa[i] = (dok && gr < N) ? X[gr * ldx + col] * wv : T(0);
+      pb[i] = (dok && gc < N2) ? Xb[gc * ldb + col] * wv : T(0);
     }
-    for (int d = 0; d < kc; ++d) {
-      T a[4], b[4];
+  };
+  auto stage = [&](int buf, int ch) {  // registers -> shared buffer `buf` (+ norms up to and including chunk ch)
+    T* dA = sA + buf * (KF_KC * KF_LD);
+    T* dB = sB + buf * (KF_KC * KF_LD);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = sA[d * KB_TILE + ty * 4 + r];
+    for (int i = 0; i < 2; ++i) {
+      dA[sd * KF_LD + sr0 + 32 * i] = pa[i];
+      dB[sd * KF_LD + sr0 + 32 * i] = pb[i];
+      T va = pa[i] * pa[i], vb = pb[i] * pb[i];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] = sB[d * KB_TILE + tx * 4 + c];
+      for (int o = 1; o < 8; o <<= 1) {
+        va += __shfl_xor_sync(0xffffffffu, va, o);
+        vb += __shfl_xor_sync(0xffffffffu, vb, o);
+      }
+      qa[i] = ch == 0 ? va : qa[i] + va;
+      qb[i] = ch == 0 ? vb : qb[i] + vb;
+      if (sd == 0) {
+        sNa[buf * KB_TILE + sr0 + 32 * i] = qa[i];
+        sNb[buf * KB_TILE + sr0 + 32 * i] = qb[i];
+      }
+    }
+  };
+
+  // software pipeline over steps (tile, chunk): compute step s from buffer s&1 while step s+1 is written to the
+  // other buffer and step s+2 is in flight from global memory; ONE barrier per step
+  // (tile coordinates are decoded once per tile, when it enters the pipeline, and handed down)
+  const int nt = (int)ntiles, G = (int)gridDim.x;
+  int t = blockIdx.x, ch = 0, by = 0, bx = 0;  // step s
+  int t1 = t, ch1 = 0, by1 = 0, bx1 = 0;       // step s+1
+  auto advance = [&](int& tt, int& cc, int& yy, int& xx) {
+    if (cc + 1 < nchunks) { ++cc; return; }
+    cc = 0;
+    tt += G;
+    if (tt < nt) decode(tt, yy, xx);
+  };
+  if (t < nt) { decode(t, by, bx); fetch(by, bx, 0); stage(0, 0); }
+  by1 = by; bx1 = bx;
+  advance(t1, ch1, by1, bx1);
+  if (t1 < nt) fetch(by1, bx1, ch1);
+  __syncthreads();
+  int buf = 0;
+  T dots[4][4];
+  while (t < nt) {
+    if (t1 < nt) stage(buf ^ 1, ch1);
+    int t2 = t1, ch2 = ch1, by2 = by1, bx2 = bx1;
+    if (t1 < nt) {
+      advance(t2, ch2, by2, bx2);
+      if (t2 < nt) fetch(by2, bx2, ch2);
+    }
+    if (ch == 0) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dots[r][c] = fma(a[r], b[c], dots[r][c]);
+        for (int c = 0; c < 4; ++c) dots[r][c] = T(0);
     }
-  }
-  __syncthreads();
+    {
+      const T* cA = sA + buf * (KF_KC * KF_LD);
+      const T* cB = sB + buf * (KF_KC * KF_LD);
+#pragma unroll
+      for (int d = 0; d < ((KF_VARIANT & 2) ? 1 : KF_KC); ++d) {
+        T a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = cA[d * KF_LD + rowi(r)];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = cB[d * KF_LD + coli(c)];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dots[r][c] = fma(a[r], b[c], dots[r][c]);
+      }
+    }
+#define KF_NEXT_STEP() do { buf ^= 1; t = t1; ch = ch1; by = by1; bx = bx1; t1 = t2; ch1 = ch2; by1 = by2; bx1 = bx2; } while (0)
+    if (ch + 1 < nchunks) {  // more dims of this tile to come
+      __syncthreads();
+      KF_NEXT_STEP();
+      continue;
+    }
+    const int64_t row0 = (int64_t)by * KB_TILE, col0 = (int64_t)bx * KB_TILE;
 
-  const T scale = T(prog.l_scale[0]), var = T(prog.l_var[0]);
-  T vals[16];
-  T na[4], nb[4];
+    T vals[16];
+    T na[4], nb[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) { na[r] = sNa[ty * 4 + r]; nb[r] = sNb[tx * 4 + r]; }
-  // fully unrolled (no local array, 32-bit index math); the sum of norms is formed FIRST so that
-  // (i,j) and (j,i) round identically and a symmetric K comes out bit-symmetric
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (sizeof(T) == 8) {
-      double r2[4], o[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) r2[c] = (double)scale * fma(-2.0, (double)dots[r][c], (double)na[r] + (double)nb[c]);
-      stationary_value4<TYPE>(r2, (double)var, s_tab, o);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) vals[r * 4 + c] = (T)o[c];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const T sn = na[r] + nb[c];
-        const T r2 = scale * fma(T(-2), dots[r][c], sn);
-        vals[r * 4 + c] = stationary_value<T, TYPE>(r2, var, s_tab);
-      }
-    }
-  }
-  if (sym && bx == by) {  // diagonal shift: only diagonal tiles carry diagonal elements
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (ty * 4 + r == tx * 4 + c) {
-          const int64_t gi = row0 + ty * 4 + r;
-          vals[r * 4 + c] += diag_scalar + ((diag_vec && gi < N) ? diag_vec[gi] : T(0));
-        }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t gi = row0 + ty * 4 + r;
-    if (gi < N) {
-      const int64_t gj0 = col0 + tx * 4;
-      T* dst = K + gi * ldk + gj0;
-      if (vec_ok && gj0 + 3 < N2) {
-        if (sizeof(T) == 8) {
-          reinterpret_cast<double2*>(dst)[0] = make_double2((double)vals[r * 4 + 0], (double)vals[r * 4 + 1]);
-          reinterpret_cast<double2*>(dst)[1] = make_double2((double)vals[r * 4 + 2], (double)vals[r * 4 + 3]);
-        } else {
-          reinterpret_cast<float4*>(dst)[0] =
-              make_float4((float)vals[r * 4 + 0], (float)vals[r * 4 + 1], (float)vals[r * 4 + 2], (float)vals[r * 4 + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (gj0 + c < N2) dst[c] = vals[r * 4 + c];
-      }
-    }
-  }
-  if (mode == 2 && bx < by) {  // mirrored tile K[col0.., row0..] = tile^T, staged for coalesced rows
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) sT[(tx * 4 + c) * KF_TS + ty * 4 + r] = vals[r * 4 + c];
-    __syncthreads();
+    for (int r = 0; r < 4; ++r) { na[r] = sNa[buf * KB_TILE + rowi(r)]; nb[r] = sNb[buf * KB_TILE + coli(r)]; }
+    // the sum of norms is formed FIRST so that (i,j) and (j,i) round identically inside a diagonal tile
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int tr = ty + 16 * r;                   // row of the transposed tile
-      const int64_t gi = col0 + tr;
-      if (gi < N2) {
-        const int64_t gj0 = row0 + tx * 4;
-        T* dst = K + gi * ldk + gj0;
-        const T* src = sT + tr * KF_TS + tx * 4;
-        if (vec_ok && gj0 + 3 < N) {
-          if (sizeof(T) == 8) {
-            reinterpret_cast<double2*>(dst)[0] = make_double2((double)src[0], (double)src[1]);
-            reinterpret_cast<double2*>(dst)[1] = make_double2((double)src[2], (double)src[3]);
-          } else {
-            reinterpret_cast<float4*>(dst)[0] = make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]);
-          }
-        } else {
+      if (sizeof(T) == 8) {
+        double r2[4], o[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (gj0 + c < N) dst[c] = src[c];
+        for (int c = 0; c < 4; ++c) r2[c] = fma(-2.0, (double)dots[r][c], (double)na[r] + (double)nb[c]);
+        if (KF_VARIANT & 4) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[c] = r2[c];
+        } else {
+          stationary_value4<TYPE>(r2, (double)var, var3, var_ok, s_tab, o);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vals[r * 4 + c] = (T)o[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const T sn = na[r] + nb[c];
+          vals[r * 4 + c] = (T)stationary_value_f32<TYPE>((float)fma(T(-2), dots[r][c], sn), (float)var);
         }
       }
     }
+    if (sym && bx == by && tx == ty) {  // diagonal shift: only diagonal micro-tiles carry diagonal elements
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t gi = row0 + rowi(r);
+        vals[r * 4 + r] += diag_scalar + ((diag_vec && gi < N) ? diag_vec[gi] : T(0));
+      }
+    }
+    if (KF_VARIANT & 1) {  // keep the values alive without the store traffic
+      T acc = T(0);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc += vals[e];
+      if (acc == T(-12345.678)) K[tid] = acc;
+      __syncthreads();
+      KF_NEXT_STEP();
+      continue;
+    }
+    const bool interior = vec_ok && row0 + KB_TILE <= N && col0 + KB_TILE <= N2;  // uniform: no per-element checks
+    if (interior) {
+      using V2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        T* dst = K + (row0 + rowi(r)) * ldk + col0 + tx * 2;
+        V2 v0, v1;
+        v0.x = vals[r * 4 + 0]; v0.y = vals[r * 4 + 1];
+        v1.x = vals[r * 4 + 2]; v1.y = vals[r * 4 + 3];
+        *reinterpret_cast<V2*>(dst) = v0;
+        *reinterpret_cast<V2*>(dst + 32) = v1;
+      }
+      if (mode == 2 && bx < by) {  // mirrored tile K[col0 + j][row0 + i] = tile[i][j]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          T* dt = K + (col0 + coli(c)) * ldk + row0 + ty * 2;
+          V2 v0, v1;
+          v0.x = vals[0 * 4 + c]; v0.y = vals[1 * 4 + c];
+          v1.x = vals[2 * 4 + c]; v1.y = vals[3 * 4 + c];
+          *reinterpret_cast<V2*>(dt) = v0;
+          *reinterpret_cast<V2*>(dt + 32) = v1;
+        }
+      }
+    } else {  // ragged edge tiles / unaligned K: element-wise guarded stores
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t gi = row0 + rowi(r);
+        if (gi < N) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (col0 + coli(c) < N2) K[gi * ldk + col0 + coli(c)] = vals[r * 4 + c];
+        }
+      }
+      if (mode == 2 && bx < by) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int64_t gi = col0 + coli(c);
+          if (gi < N2) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (row0 + rowi(r) < N) K[gi * ldk + row0 + rowi(r)] = vals[r * 4 + c];
+          }
+        }
+      }
+    }
+    __syncthreads();  // every reader of buffer `buf` is done; the other buffer is completely written
+    KF_NEXT_STEP();
   }
+#undef KF_NEXT_STEP
 }
 
 static bool fast_path_ok(const KProg& p) {
@@ -685,21 +747,23 @@ static bool fast_path_ok(const KProg& p) {
   return t == GPK_K_RBF || t == GPK_K_MATERN12 || t == GPK_K_MATERN32 || t == GPK_K_MATERN52 || t == GPK_K_EXPONENTIAL;
 }
 
-template <typename T, int TYPE>
+template <typename T, int TYPE, int MINB>
 static int kbuild_fast_go(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2,
                           void* K, int64_t ldk, int mode, double diag_scalar, const void* diag_vec, int vec_ok,
                           cudaStream_t st) {
-  const size_t smem = (size_t)(2 * KB_KC * KB_TILE + 2 * KB_TILE + KB_TILE * KF_TS) * sizeof(T);
-  static bool attr = false;
-  if (!attr) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(kbuild_fast_kernel<T, TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   const int64_t nty = (N + KB_TILE - 1) / KB_TILE, ntx = (N2 + KB_TILE - 1) / KB_TILE;
   const int64_t ntiles = mode == 0 ? nty * ntx : nty * (nty + 1) / 2;
-  GPK_CHECK_ARG(ntiles < (1ll << 31), "kbuild: too many tiles");
-  kbuild_fast_kernel<T, TYPE><<<(unsigned)ntiles, 256, smem, st>>>(p, (const T*)X, N, ldx, (const T*)X2, N2, ldx2, (T*)K,
-                                                                    ldk, mode, (T)diag_scalar, (const T*)diag_vec, vec_ok);
+  static int grid_max = 0;  // persistent grid: resident CTAs per SM x SM count
+  if (!grid_max) {
+    int dev = 0, sms = 0, per_sm = 0;
+    GPK_CUDA_OK(cudaGetDevice(&dev));
+    GPK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kbuild_fast_kernel<T, TYPE, MINB>, 256, 0));
+    grid_max = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int64_t grid = ntiles < grid_max ? ntiles : grid_max;
+  kbuild_fast_kernel<T, TYPE, MINB><<<(unsigned)grid, 256, 0, st>>>(p, (const T*)X, N, ldx, (const T*)X2, N2, ldx2, (T*)K, ldk,
+                                                               mode, (T)diag_scalar, (const T*)diag_vec, vec_ok, ntiles);
   GPK_LAUNCH_OK();
   return 0;
 }
@@ -716,7 +780,20 @@ static int kbuild_fast_launch(const KProg& p, const void* X, int64_t N, int64_t 
   ProfScope ps(PROF_KBUILD, st);
   const int vec_ok = ((uintptr_t)K % 16 == 0) && ((ldk * sizeof(T)) % 16 == 0);
   const int mode = p.symmetric ? (lower ? 1 : 2) : 0;
-#define GPK_KF(TY) return kbuild_fast_go<T, TY>(p, X, N, ldx, X2, N2, ldx2, K, ldk, mode, diag_scalar, diag_vec, vec_ok, st)
+  // resident CTAs per SM the kernel is compiled for: 2 (<= 128 registers) or 3 (<= 80); GPK_KF_MINB overrides
+  static const bool minb2 = []() { const char* e = getenv("GPK_KF_MINB"); return e ? e[0] == '2' : sizeof(T) == 8; }();
+  // fold c / lengthscale^2 into the per-dimension weights (applied to both operands): x = c r2 comes out of
+  // the norm expansion with no further scaling
+#define GPK_KF(TY)                                                                                         \
+  do {                                                                                                     \
+    KProg q = p;                                                                                           \
+    const double f = sqrt(q.l_scale[0] * kf_fold<TY>());                                                   \
+    for (int d = 0; d < q.g_ndims[0]; ++d) q.w[d] *= f;                                                    \
+    q.l_scale[0] = 1.0;                                                                                    \
+    if (minb2)                                                                                             \
+      return kbuild_fast_go<T, TY, 2>(q, X, N, ldx, X2, N2, ldx2, K, ldk, mode, diag_scalar, diag_vec, vec_ok, st); \
+    return kbuild_fast_go<T, TY, 3>(q, X, N, ldx, X2, N2, ldx2, K, ldk, mode, diag_scalar, diag_vec, vec_ok, st); \
+  } while (0)
   switch (p.l_type[0]) {
     case GPK_K_RBF: GPK_KF(GPK_K_RBF);
     case GPK_K_MATERN12: GPK_KF(GPK_K_MATERN12);
