@@ -96,7 +96,7 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
 
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
-            cudaStream_t st);
+            cudaStream_t st, bool need_dinv = true);
 
 // tcgen05 (int8-sliced fp64) symmetric rank-k update, gemm_tc.cu
 bool tc_enabled();

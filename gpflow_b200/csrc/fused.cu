@@ -61,7 +61,8 @@ int gpr_lml(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const doub
   // (Y - m)^T as P extra rows: the factorisation's panel solves turn them into alpha^T (logdensities.py:150)
   char* Yrows = (char*)w.A + (size_t)N * w.lda * ts;
   GPK_TRY(transpose_impl(Yc, N, P, P, Yrows, w.lda, dtype, st));
-  GPK_TRY(potrf_any(w.A, N, N + P, w.lda, dtype, w.info, w.dinv, st));  // gpr.py:102
+  // alpha comes out of the factorisation itself (extra rows): no trsm on this factor, block inverses not needed
+  GPK_TRY(potrf_any(w.A, N, N + P, w.lda, dtype, w.info, w.dinv, st, /*need_dinv=*/false));  // gpr.py:102
   GPK_CUDA_OK(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
   for (int64_t p = 0; p < P; ++p)
     GPK_TRY(reduce_impl(1, Yrows + (size_t)p * w.lda * ts, N, 1, 1.0, 1, out + 1, dtype, st));

@@ -141,7 +141,7 @@ __device__ __forceinline__ void mt_zero(T (&acc)[4][4]) {
 //   level 32: inside each 64x64 diagonal block (2 independent pairs, 64 threads each, 2 products)
 //   level 64: the 64x64 block (rows 64.., cols 0..63) with all 256 threads (2 products of depth 64)
 template <typename T>
-__device__ void invert_offdiag_128(T* S, T* tmp) {
+__device__ void invert_offdiag_128(T* S, T* tmp, bool level64 = true) {
   const int tid = threadIdx.x;
   T acc[4][4];
   {  // ---- level 32: pairs (I,J) = (1,0) and (3,2)
@@ -175,7 +175,7 @@ __device__ void invert_offdiag_128(T* S, T* tmp) {
     }
     __syncthreads();
   }
-  {  // ---- level 64: X = -D^-1 (C A^-1), C = L[64:128, 0:64], A^-1 = Linv[0:64,0:64], D^-1 = Linv[64:,64:]
+  if (level64) {  // ---- level 64: X = -D^-1 (C A^-1), C = L[64:128, 0:64], A^-1 = Linv[0:64,0:64], D^-1 = Linv[64:,64:]
     const int tr = tid >> 4, tc = tid & 15;            // 16 x 16 threads, rows tr + 16 i, cols tc + 16 j
     mt_zero(acc);
     const T* Ca = S + (64 + tr) * LS;                  // C[r][k] = S[64+r][k]
@@ -229,8 +229,23 @@ __device__ __forceinline__ void write_dinv(const T* S, T* __restrict__ dinv) {
   }
 }
 
-// ---- leaf: factor + invert one diagonal block (n <= 128) ------------------------------------------
+// inverses of the two 64x64 diagonal sub-blocks only: dinv64[b][r][c], b = 0, 1 (slim leaf, see potrf_panel_kernel)
 template <typename T>
+__device__ __forceinline__ void write_dinv64(const T* S, T* __restrict__ dinv) {
+  const int c = threadIdx.x & 63, rq = threadIdx.x >> 6;  // 4 rows per pass
+#pragma unroll 4
+  for (int e = 0; e < 32; ++e) {
+    const int b = e >> 4, r = (e & 15) * 4 + rq;
+    dinv[b * 4096 + r * 64 + c] = c <= r ? S[(64 * b + c) * LS + 64 * b + r] : T(0);
+  }
+}
+
+// ---- leaf: factor + invert one diagonal block (n <= 128) ------------------------------------------
+// SLIM = false: leaves the full 128x128 inverse of the block in dinv (inverse-based panel solve by one GEMM).
+// SLIM = true : leaves only the inverses of the two 64x64 diagonal sub-blocks ([2][64][64]); the rows below are
+//               solved by potrf_panel_kernel, which needs no more, and the 64x64 off-diagonal block of the
+//               inverse (two 64^3 products on ONE SM, ~13 us) leaves the critical path of the factorisation.
+template <typename T, bool SLIM>
 __global__ void __launch_bounds__(256, 1)
 potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base,
                   long long* dbg, int* wait_flag, int wait_target) {
@@ -265,32 +280,34 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
       const int bad = warp_chol32<T>(S, jb, ldiag);
       if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + jb + bad);
       if (J == 0) GPK_DBG(2);
-      warp_inv32<T>(S, jb);
-      if (J == 0) GPK_DBG(3);
     }
     __syncthreads();
+    if (J == 0) GPK_DBG(3);
     const int t0 = jb + 32, nr = NB - t0;
     if (nr > 0) {
-      // panel rows t0..127:  X = B inv(L_JJ)^T ; inv(L_JJ)[c][k] = S[jb+k][jb+c] for k <= c
-      T acc[4][4];
-      const int ni = nr / 32;  // row groups of 32 owned by this thread grid
-      {
-        mt_zero(acc);
-        const T* Bp = S + (t0 + tr) * LS + jb;
-        const T* Ip = S + jb * LS + jb + tc;
-        mt_acc<T>(acc, 0, 32,
-                  [&](int i, int k) { return i < ni ? Bp[i * 32 * LS + k] : T(0); },
-                  [&](int j, int k) { const T v = Ip[k * LS + 8 * j]; return k <= tc + 8 * j ? v : T(0); });
+      // panel rows t0..127:  X = B L_JJ^-T by forward substitution, ONE THREAD PER ROW with the row's 32 entries
+      // in registers; L_JJ (strict lower part) and 1/diag are warp-wide broadcasts from shared memory.  Replaces
+      // the serial 32x32 inverse + product of earlier versions: ~1.6k cycles instead of ~7k per J.
+      if (tid < nr) {
+        T* rowp = S + (t0 + tid) * LS + jb;
+        const T* Lj = S + jb * LS + jb;
+        T b[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < ni)
+        for (int k = 0; k < 32; ++k) b[k] = rowp[k];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tmp[(tr + 32 * i) * 32 + tc + 8 * j] = acc[i][j];
+        for (int k = 0; k < 32; ++k) {
+          const T xk = b[k] * Lj[k * LS + k];  // diagonal slot holds 1/L_kk
+          b[k] = xk;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j > k) b[j] = fma(-xk, Lj[j * LS + k], b[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rowp[k] = b[k];
       }
       __syncthreads();
-      for (int e = tid; e < nr * 32; e += 256) S[(t0 + (e >> 5)) * LS + jb + (e & 31)] = tmp[e];
-      __syncthreads();
       if (J == 0) GPK_DBG(4);
+      T acc[4][4];
       // trailing update by 32x32 block pairs (rb >= cb), 64 threads (8x8 interleaved 4x4 micro-tiles)
       // per pair:  C[r][c] -= sum_k S[r][jb+k] S[c][jb+k]
       {
@@ -332,13 +349,118 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
     }
   }
   GPK_DBG(7);
-  invert_offdiag_128<T>(S, tmp);
+  if (tid < 128) warp_inv32<T>(S, (tid >> 5) * 32);  // the four 32x32 diagonal inverses, one warp each
+  __syncthreads();
+  invert_offdiag_128<T>(S, tmp, !SLIM);
   GPK_DBG(8);
-  write_dinv<T>(S, dinv);
+  if (SLIM) write_dinv64<T>(S, dinv); else write_dinv<T>(S, dinv);
   __syncthreads();
   GPK_DBG(9);
 #undef GPK_DBG
 }
+
+// ---- panel solve below a diagonal block (fp64): X = B L^-T for 64 rows per CTA -------------------------
+// With L = [A 0; C D] (64x64 blocks):  X1 = B1 A^-T,  T = B2 - X1 C^T,  X2 = T D^-T  -- three 64-deep products on
+// DMMA (mma.sync.m8n8k4.f64), the triangular ones skipping their zero k-blocks.  Each WARP owns 8 rows through
+// all three phases (operands A^-1, C, D^-1 are CTA-shared and read-only), so the phases need only __syncwarp.
+constexpr int PR = 64;    // panel rows per CTA
+constexpr int PLB = 132;  // row stride of the staged panel rows (= 4 mod 16: minimal-wavefront fragment loads)
+constexpr int PLW = 68;   // row stride of the 64-wide operands
+
+__device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const double* __restrict__ Lblk, int64_t ldl,
+                   int nb, const double* __restrict__ dinv64) {
+  extern __shared__ __align__(16) unsigned char leaf_smem[];
+  double* Bs = reinterpret_cast<double*>(leaf_smem);  // [64][PLB]
+  double* Ai = Bs + PR * PLB;                          // [64][PLW]  A^-1
+  double* Di = Ai + 64 * PLW;                          // [64][PLW]  D^-1
+  double* Cs = Di + 64 * PLW;                          // [64][PLW]  C = L[64:128, 0:64]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int64_t r0 = (int64_t)blockIdx.x * PR;
+  for (int e = tid; e < 4096; e += 256) {
+    const int i = e >> 6, j = e & 63;
+    Ai[i * PLW + j] = dinv64[e];
+    Di[i * PLW + j] = dinv64[4096 + e];
+    Cs[i * PLW + j] = (64 + i < nb) ? Lblk[(int64_t)(64 + i) * ldl + j] : 0.0;
+  }
+  double* Bw = Bs + (w * 8) * PLB;  // this warp's 8 rows
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int64_t row = r0 + w * 8 + rr;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = lane + 32 * cc;
+      Bw[rr * PLB + c] = (row < rows && c < nb) ? B[row * ldb + c] : 0.0;
+    }
+  }
+  __syncthreads();
+
+  double acc[8][2], af[16];
+  // ---- phase 1: X1 = B1 A^-T;  (A^-T)[k][n] = Ai[n][k], zero for k > n
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) af[ks] = Bw[g * PLB + ks * 4 + q];
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    acc[cb][0] = acc[cb][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2 * (cb + 1); ++ks) dmma884p(acc[cb], af[ks], Ai[(cb * 8 + g) * PLW + ks * 4 + q]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+    *reinterpret_cast<double2*>(Bw + g * PLB + cb * 8 + 2 * q) = make_double2(acc[cb][0], acc[cb][1]);
+  __syncwarp();
+  // ---- phase 2: T = B2 - X1 C^T
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) af[ks] = -Bw[g * PLB + ks * 4 + q];
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    const double2 b2 = *reinterpret_cast<const double2*>(Bw + g * PLB + 64 + cb * 8 + 2 * q);
+    acc[cb][0] = b2.x;
+    acc[cb][1] = b2.y;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) dmma884p(acc[cb], af[ks], Cs[(cb * 8 + g) * PLW + ks * 4 + q]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+    *reinterpret_cast<double2*>(Bw + g * PLB + 64 + cb * 8 + 2 * q) = make_double2(acc[cb][0], acc[cb][1]);
+  __syncwarp();
+  // ---- phase 3: X2 = T D^-T
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) af[ks] = Bw[g * PLB + 64 + ks * 4 + q];
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) {
+    acc[cb][0] = acc[cb][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2 * (cb + 1); ++ks) dmma884p(acc[cb], af[ks], Di[(cb * 8 + g) * PLW + ks * 4 + q]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+    *reinterpret_cast<double2*>(Bw + g * PLB + 64 + cb * 8 + 2 * q) = make_double2(acc[cb][0], acc[cb][1]);
+  __syncwarp();
+  // ---- own rows back to global
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int64_t row = r0 + w * 8 + rr;
+    if (row < rows) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = lane + 32 * cc;
+        if (c < nb) B[row * ldb + c] = Bw[rr * PLB + c];
+      }
+    }
+  }
+}
+
+static size_t panel_smem_bytes() { return (size_t)(PR * PLB + 3 * 64 * PLW) * sizeof(double); }
 
 // ---- standalone inverse of the diagonal blocks of a given factor (for trsm without cached dinv) -----
 template <typename T>
@@ -367,8 +489,12 @@ template <typename T>
 static int leaf_attr() {
   static bool done = false;
   if (!done) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(potrf_leaf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GPK_CUDA_OK(cudaFuncSetAttribute(potrf_leaf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)leaf_smem_bytes<T>()));
+    GPK_CUDA_OK(cudaFuncSetAttribute(potrf_leaf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)leaf_smem_bytes<T>()));
+    GPK_CUDA_OK(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)panel_smem_bytes()));
     GPK_CUDA_OK(cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)leaf_smem_bytes<T>()));
     done = true;
@@ -391,6 +517,7 @@ struct LookAhead {
   int target = 0;
   bool pending = false;
   bool enabled = false;
+  bool slim = false;       // fp64, n > 128: slim leaves + potrf_panel_kernel (full block inverses filled in afterwards)
 };
 
 static bool lookahead_enabled() {
@@ -469,12 +596,24 @@ static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, 
     }
     {
       ProfScope ps(PROF_LEAF, ls);
-      potrf_leaf_kernel<T><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+      if (la.slim)
+        potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+      else
+        potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
       GPK_LAUNCH_OK();
     }
     if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
-    if (rows > n)  // rows below: X = B L^-T = B Linv^T, in place (single column tile)
-      GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, ls));
+    if (rows > n) {  // rows below: X = B L^-T, in place
+      if (la.slim) {
+        ProfScope ps(PROF_GEMM, ls);
+        const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
+        potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(), ls>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
+                                                                   (int)n, (const double*)dblk);
+        GPK_LAUNCH_OK();
+      } else {  // one GEMM with the block inverse (single column tile)
+        GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, ls));
+      }
+    }
     if (la.pending) {
       GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
       GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));  // main stream joins (it also still holds U)
@@ -489,9 +628,15 @@ static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, 
   return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, tcws, tcws_bytes, la, st);
 }
 
+static bool slim_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_SLIM_LEAF"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
-            cudaStream_t st) {
+            cudaStream_t st, bool need_dinv) {
   if (n <= 0) return 0;
   GPK_TRY(leaf_attr<T>());
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
@@ -499,7 +644,12 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   // the look-ahead counter lives in the last 256 bytes of the dinv area's alignment slack (see potrf_ws_bytes)
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(dinv) + (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(T));
   if (n > NB) GPK_TRY(lookahead_init(la, flag, st));
-  return potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, la, st);
+  la.slim = sizeof(T) == 8 && n > NB && slim_enabled();
+  GPK_TRY(potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, la, st));
+  // slim leaves left only the 64x64 diagonal inverses: the full 128x128 block inverses that gpk_trsm consumes are
+  // computed now, all blocks in parallel, off the factorisation's critical path (skipped when nobody will use them)
+  if (la.slim && need_dinv) GPK_TRY(trtri_diag_t<T>(A, n, lda, dinv, st));
+  return 0;
 }
 
 template <typename T>
@@ -544,13 +694,13 @@ int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, in
 // phase timing of one leaf launch (clock64 at phase boundaries), for tuning
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
   GPK_TRY(leaf_attr<double>());
-  potrf_leaf_kernel<double><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0);
+  potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0);
   GPK_LAUNCH_OK();
   return 0;
 }
 
-template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, void*, size_t, cudaStream_t);
-template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, void*, size_t, cudaStream_t);
+template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, void*, size_t, cudaStream_t, bool);
+template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, void*, size_t, cudaStream_t, bool);
 template int trtri_diag_t<float>(const float*, int64_t, int64_t, float*, cudaStream_t);
 template int trtri_diag_t<double>(const double*, int64_t, int64_t, double*, cudaStream_t);
 template int trsm_t<float>(int, const float*, int64_t, int64_t, float*, int64_t, int64_t, const float*, cudaStream_t);
