@@ -49,9 +49,8 @@ template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rs
 
 // ---- 32x32 diagonal block Cholesky by one warp: lane i owns row i in registers ---------------------
 // On return S holds L (strict lower part), ldiag the diagonal of L, and S's diagonal 1/L_kk.
-// Cross-lane traffic is shuffles only (measured: 11.5k cycles; a shared-memory column broadcast
-// variant took 18.4k, a pure shared-memory loop 27k).  Chain per column: shfl -> rsqrt -> mul ->
-// shfl -> fma.
+// Cross-lane traffic is shuffles only (a shared-memory column broadcast variant took 18.4k cycles, a pure
+// shared-memory loop 27k, the right-looking register version 10-11.5k).
 template <typename T>
 __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   const int lane = threadIdx.x & 31;
@@ -60,6 +59,9 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   for (int c = 0; c < 32; ++c) a[c] = c <= lane ? S[(jb + lane) * LS + jb + c] : T(0);
   int bad = 0;
   T my_inv = T(1), my_diag = T(1);
+  // Right-looking, fully unrolled: 10k cycles per 32x32 block on B200.  Tried and rejected (measured): 8-column
+  // blocking (10.0k, no change), left-looking columns with four split partial sums (13.6k), shared-memory column
+  // broadcast (18.4k).  The block is bound by the 1056 SHFL.32 + 528 DFMA issue of one warp, not by the pivot chain.
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     T d = __shfl_sync(0xffffffffu, a[k], k);
@@ -202,20 +204,20 @@ __device__ void invert_offdiag_128(T* S, T* tmp, bool level64 = true) {
   }
 }
 
-// coalesced, 16-deep unrolled load of the lower triangle of an n x n block (identity-padded to 128)
+// coalesced, 32-deep unrolled load of the lower triangle of an n x n block (identity-padded to 128)
 template <typename T>
 __device__ __forceinline__ void load_lower_block(T* S, const T* __restrict__ A, int64_t lda, int n) {
   const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;  // 2 rows per pass
 #pragma unroll 1
-  for (int r0 = 0; r0 < NB; r0 += 32) {
-    T v[16];
+  for (int r0 = 0; r0 < NB; r0 += 64) {
+    T v[32];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < 32; ++u) {
       const int r = r0 + 2 * u + rh;
       v[u] = (r < n && c <= r) ? A[(int64_t)r * lda + c] : ((r >= n && c == r) ? T(1) : T(0));
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) S[(r0 + 2 * u + rh) * LS + c] = v[u];
+    for (int u = 0; u < 32; ++u) S[(r0 + 2 * u + rh) * LS + c] = v[u];
   }
 }
 
@@ -273,21 +275,18 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   __syncthreads();
   GPK_DBG(1);
 
+  // Per 32-column step J: rows below by substitution, trailing update with IN-LEAF LOOK-AHEAD -- the first block
+  // pair of the update is the next diagonal block, and as soon as the two warps that own it are done (named
+  // barrier) warp 0 factors it while the other warps finish the update.  Step -1 only factors block 0.  (One call
+  // site per phase: the fully unrolled phases are large and the kernel must stay inside the instruction cache.)
 #pragma unroll 1
-  for (int J = 0; J < 4; ++J) {
+  for (int J = -1; J < 3; ++J) {
     const int jb = J * 32;
-    if (tid < 32) {
-      const int bad = warp_chol32<T>(S, jb, ldiag);
-      if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + jb + bad);
-      if (J == 0) GPK_DBG(2);
-    }
-    __syncthreads();
-    if (J == 0) GPK_DBG(3);
     const int t0 = jb + 32, nr = NB - t0;
-    if (nr > 0) {
+    const int grp = tid >> 6;
+    if (J >= 0) {
       // panel rows t0..127:  X = B L_JJ^-T by forward substitution, ONE THREAD PER ROW with the row's 32 entries
-      // in registers; L_JJ (strict lower part) and 1/diag are warp-wide broadcasts from shared memory.  Replaces
-      // the serial 32x32 inverse + product of earlier versions: ~1.6k cycles instead of ~7k per J.
+      // in registers; L_JJ (strict lower part) and 1/diag are warp-wide broadcasts from shared memory
       if (tid < nr) {
         T* rowp = S + (t0 + tid) * LS + jb;
         const T* Lj = S + jb * LS + jb;
@@ -307,45 +306,61 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
       }
       __syncthreads();
       if (J == 0) GPK_DBG(4);
-      T acc[4][4];
-      // trailing update by 32x32 block pairs (rb >= cb), 64 threads (8x8 interleaved 4x4 micro-tiles)
-      // per pair:  C[r][c] -= sum_k S[r][jb+k] S[c][jb+k]
-      {
-        const int nblk = nr / 32, npairs = nblk * (nblk + 1) / 2;
-        const int grp = tid >> 6, sub = tid & 63, ptr_ = sub >> 3, ptc = sub & 7;
-        for (int pr = grp; pr < npairs; pr += 4) {
-          int rbk = 0, rem = pr;
-          while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
-          const int cbk = rem;
-          const int R0 = t0 + rbk * 32, C0 = t0 + cbk * 32;
-          mt_zero(acc);
-          const T* Ra = S + (R0 + ptr_) * LS + jb;
-          const T* Rb = S + (C0 + ptc) * LS + jb;
-          mt_acc<T>(acc, 0, 32,
-                    [&](int i, int k) { return Ra[i * 8 * LS + k]; },
-                    [&](int j, int k) { return Rb[j * 8 * LS + k]; });
+      // trailing update by 32x32 block pairs (rb >= cb), 64 threads (8x8 interleaved 4x4 micro-tiles) per pair:
+      //   C[r][c] -= sum_k S[r][jb+k] S[c][jb+k];   pair 0 = the next diagonal block, done by warps 0-1 only
+      const int nblk = nr / 32, npairs = nblk * (nblk + 1) / 2;
+      const int sub = tid & 63, ptr_ = sub >> 3, ptc = sub & 7;
+      int pr = grp;
+      while (pr < npairs) {
+        int rbk = 0, rem = pr;
+        while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
+        const int cbk = rem;
+        const int R0 = t0 + rbk * 32, C0 = t0 + cbk * 32;
+        T acc[4][4];
+        mt_zero(acc);
+        const T* Ra = S + (R0 + ptr_) * LS + jb;
+        const T* Rb = S + (C0 + ptc) * LS + jb;
+        mt_acc<T>(acc, 0, 32,
+                  [&](int i, int k) { return Ra[i * 8 * LS + k]; },
+                  [&](int j, int k) { return Rb[j * 8 * LS + k]; });
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int r = R0 + ptr_ + 8 * i, c = C0 + ptc + 8 * j;
-              if (c <= r) S[r * LS + c] -= acc[i][j];
-            }
-        }
+          for (int j = 0; j < 4; ++j) {
+            const int r = R0 + ptr_ + 8 * i, c = C0 + ptc + 8 * j;
+            if (c <= r) S[r * LS + c] -= acc[i][j];
+          }
+        if (grp == 0) break;              // warps 0-1 go on to the next diagonal block
+        pr = pr < 4 ? 3 + grp : pr + 3;   // the other three groups share the remaining pairs
       }
-      __syncthreads();
-      if (J == 0) GPK_DBG(5);
+      if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");  // the next diagonal block is up to date
     }
+    if (tid < 32) {
+      const int bad = warp_chol32<T>(S, t0, ldiag);
+      if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + t0 + bad);
+    }
+    __syncthreads();
+    if (J == -1) { GPK_DBG(2); GPK_DBG(3); }
+    if (J == 0) GPK_DBG(5);
   }
   GPK_DBG(6);
 
   // L back to global (lower part of the first n rows), coalesced along columns
   {
     const int c = tid & 127, rh = tid >> 7;
-#pragma unroll 8
-    for (int r0 = 0; r0 < NB; r0 += 2) {
-      const int r = r0 + rh;
-      if (r < n && c <= r) A[(int64_t)r * lda + c] = c == r ? ldiag[r] : S[r * LS + c];
+#pragma unroll 1
+    for (int r0 = 0; r0 < NB; r0 += 64) {
+      T v[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const int r = r0 + 2 * u + rh;
+        v[u] = c == r ? ldiag[r] : S[r * LS + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const int r = r0 + 2 * u + rh;
+        if (r < n && c <= r) A[(int64_t)r * lda + c] = v[u];
+      }
     }
   }
   GPK_DBG(7);
@@ -406,11 +421,11 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) af[ks] = Bw[g * PLB + ks * 4 + q];
 #pragma unroll
-  for (int cb = 0; cb < 8; ++cb) {
-    acc[cb][0] = acc[cb][1] = 0.0;
+  for (int cb = 0; cb < 8; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < 2 * (cb + 1); ++ks) dmma884p(acc[cb], af[ks], Ai[(cb * 8 + g) * PLW + ks * 4 + q]);
-  }
+  for (int ks = 0; ks < 16; ++ks)  // k outer: consecutive DMMAs hit different accumulators (no dependent issue)
+#pragma unroll
+    for (int cb = ks >> 1; cb < 8; ++cb) dmma884p(acc[cb], af[ks], Ai[(cb * 8 + g) * PLW + ks * 4 + q]);
   __syncwarp();
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb)
@@ -424,9 +439,11 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     const double2 b2 = *reinterpret_cast<const double2*>(Bw + g * PLB + 64 + cb * 8 + 2 * q);
     acc[cb][0] = b2.x;
     acc[cb][1] = b2.y;
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks) dmma884p(acc[cb], af[ks], Cs[(cb * 8 + g) * PLW + ks * 4 + q]);
   }
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) dmma884p(acc[cb], af[ks], Cs[(cb * 8 + g) * PLW + ks * 4 + q]);
   __syncwarp();
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb)
@@ -436,11 +453,11 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) af[ks] = Bw[g * PLB + 64 + ks * 4 + q];
 #pragma unroll
-  for (int cb = 0; cb < 8; ++cb) {
-    acc[cb][0] = acc[cb][1] = 0.0;
+  for (int cb = 0; cb < 8; ++cb) acc[cb][0] = acc[cb][1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < 2 * (cb + 1); ++ks) dmma884p(acc[cb], af[ks], Di[(cb * 8 + g) * PLW + ks * 4 + q]);
-  }
+  for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+    for (int cb = ks >> 1; cb < 8; ++cb) dmma884p(acc[cb], af[ks], Di[(cb * 8 + g) * PLW + ks * 4 + q]);
   __syncwarp();
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb)
@@ -504,7 +521,12 @@ static int leaf_attr() {
 
 static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
 
-constexpr int64_t TC_MIN_K = 512;  // below this the DMMA kernel wins (epilogue + slicing overhead)
+// Updates with K below this use the DMMA kernel (slicing + epilogue overhead of the int8 path); GPK_TC_MIN_K overrides.
+static int64_t tc_min_k() {
+  static int64_t v = 0;
+  if (!v) { const char* e = getenv("GPK_TC_MIN_K"); v = e ? atoll(e) : 512; if (v < 128) v = 128; }
+  return v;
+}
 
 // ---- look-ahead context ------------------------------------------------------------------------------
 // The trailing update U (main stream) and the next diagonal-block factorisation (side stream) overlap:
@@ -556,7 +578,7 @@ template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,
                            size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
   GemmOpts opts;
-  const bool use_tc = sizeof(T) == 8 && tcws && tc_enabled() && K >= TC_MIN_K && K % 32 == 0 && n <= m &&
+  const bool use_tc = sizeof(T) == 8 && tcws && tc_enabled() && K >= tc_min_k() && K % 32 == 0 && n <= m &&
                       tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices());
   if (la.enabled) {
     GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 2 * sizeof(int), st));
@@ -575,7 +597,7 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
 }
 
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
-  if (dtype != GPK_F64 || n < 2 * TC_MIN_K) return 0;
+  if (dtype != GPK_F64 || n < 2 * 128) return 0;  // sized for any GPK_TC_MIN_K >= 128
   return syrk_tc_ws_bytes(rows, ((n / NB + 1) / 2) * NB, 8);
 }
 
