@@ -206,61 +206,77 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* A,
 // ------------------------------------------------------------------------------------------------
 constexpr int SK = 8;
 
-template <typename T, bool TA, bool TB>
+// BM x BN tile, 16 x 16 threads, (BM/16) x (BN/16) accumulators per thread in groups of up to 4 consecutive
+// rows / columns.  Narrow shapes (32/64 x 128, 128 x 32/64) exist for the same reason as in the DMMA kernel: the
+// small-K GEMMs of the factorisation and of trsm have few 128 x 128 tiles (measured before: 54 launches = 2.0 ms of
+// the 5.7 ms SVGP evaluation at 2.6 TFLOP/s), and the in-place contract needs one tile across the aliased operand.
+template <typename T, bool TA, bool TB, int BM, int BN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
                  const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, int* head_flag) {
-  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * GB;
-  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * GB;
-  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + GB - 1) return;
-  __shared__ __align__(16) T sA[2][SK][GB + 4];
-  __shared__ __align__(16) T sB[2][SK][GB + 4];
-  __shared__ T s_col[GB];
+  constexpr int TM = BM / 16, TN = BN / 16, GM = TM < 4 ? TM : 4, GN = TN < 4 ? TN : 4;
+  const int64_t m0 = (int64_t)(head_flag ? blockIdx.x : blockIdx.y) * BM;
+  const int64_t n0 = (int64_t)(head_flag ? blockIdx.y : blockIdx.x) * BN;
+  if ((flags & GPK_GEMM_LOWER_ONLY) && n0 > m0 + BM - 1) return;
+  __shared__ __align__(16) T sA[2][SK][BM + 4];
+  __shared__ __align__(16) T sB[2][SK][BN + 4];
+  __shared__ T s_col[BN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  auto rowi = [&](int i) { return (i / GM) * (16 * GM) + ty * GM + (i % GM); };  // tile row of accumulator row i
+  auto coli = [&](int j) { return (j / GN) * (16 * GN) + tx * GN + (j % GN); };
 
   int64_t kb = 0, ke = k;
   const int triA = (flags & GPK_GEMM_A_LOWER) ? 1 : 0;
   if (triA) {
-    if (TA) kb = (m0 / SK) * SK; else ke = min(k, m0 + GB);
+    if (TA) kb = (m0 / SK) * SK; else ke = min(k, m0 + BM);
   }
-  T acc[8][8];
+  T acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = T(0);
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
 
-  T ra[4], rb[4];
+  constexpr int LA = BM * SK / 256, LB = BN * SK / 256;  // elements of each operand chunk per thread
+  T ra[LA], rb[LB];
   auto gload = [&](int64_t k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 256;  // 0..1023 = 128 x 8
-      {
-        int rr, kk;
-        if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; }
-        const int64_t gr = m0 + rr, gk = k0 + kk;
-        T v = T(0);
-        if (gr < m && gk < ke) {
-          const int64_t srow = !TA ? gr : gk, scol = !TA ? gk : gr;
-          if (!(triA && scol > srow)) v = A[srow * lda + scol];
-        }
-        ra[i] = v;
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * 256;
+      int rr, kk;
+      if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % BM; kk = e / BM; }
+      const int64_t gr = m0 + rr, gk = k0 + kk;
+      T v = T(0);
+      if (gr < m && gk < ke) {
+        const int64_t srow = !TA ? gr : gk, scol = !TA ? gk : gr;
+        if (!(triA && scol > srow)) v = A[srow * lda + scol];
       }
-      {
-        int rr, kk;
-        if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; }
-        const int64_t gr = n0 + rr, gk = k0 + kk;
-        T v = T(0);
-        if (gr < n && gk < ke) v = TB ? B[gr * ldb + gk] : B[gk * ldb + gr];
-        rb[i] = v;
-      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * 256;
+      int rr, kk;
+      if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % BN; kk = e / BN; }
+      const int64_t gr = n0 + rr, gk = k0 + kk;
+      T v = T(0);
+      if (gr < n && gk < ke) v = TB ? B[gr * ldb + gk] : B[gk * ldb + gr];
+      rb[i] = v;
     }
   };
   auto sstore = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < LA; ++i) {
       const int e = tid + i * 256;
-      { int rr, kk; if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; } sA[buf][kk][rr] = ra[i]; }
-      { int rr, kk; if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % GB; kk = e / GB; } sB[buf][kk][rr] = rb[i]; }
+      int rr, kk;
+      if (!TA) { kk = e % SK; rr = e / SK; } else { rr = e % BM; kk = e / BM; }
+      sA[buf][kk][rr] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * 256;
+      int rr, kk;
+      if (TB) { kk = e % SK; rr = e / SK; } else { rr = e % BN; kk = e / BN; }
+      sB[buf][kk][rr] = rb[i];
     }
   };
 
@@ -272,50 +288,47 @@ gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t l
     if (c + 1 < nchunks) gload(kb + (int64_t)(c + 1) * SK);
 #pragma unroll
     for (int kk = 0; kk < SK; ++kk) {
-      T a[8], b[8];
+      T a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a[i] = sA[cur][kk][ty * 4 + i];
-        a[4 + i] = sA[cur][kk][64 + ty * 4 + i];
-        b[i] = sB[cur][kk][tx * 4 + i];
-        b[4 + i] = sB[cur][kk][64 + tx * 4 + i];
-      }
+      for (int i = 0; i < TM; ++i) a[i] = sA[cur][kk][rowi(i)];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < TN; ++j) b[j] = sB[cur][kk][coli(j)];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     if (c + 1 < nchunks) sstore(cur ^ 1);
     __syncthreads();
   }
 
   if (flags & GPK_GEMM_COLSUMSQ) {
-    if (tid < GB) s_col[tid] = T(0);
+    if (tid < BN) s_col[tid] = T(0);
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < TN; ++j) {
       T s = T(0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t gi = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+      for (int i = 0; i < TM; ++i) {
+        const int64_t gi = m0 + rowi(i);
         const T v = alpha * acc[i][j];
         if (gi < m) s += v * v;
       }
       s += __shfl_xor_sync(0xffffffffu, s, 16);  // the two ty rows held by one warp
-      if ((tid & 16) == 0) atomic_add_t(&s_col[j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4], s);
+      if ((tid & 16) == 0) atomic_add_t(&s_col[coli(j)], s);
     }
     __syncthreads();
-    if (tid < GB && n0 + tid < n) atomic_add_t(&C[n0 + tid], s_col[tid]);
+    if (tid < BN && n0 + tid < n) atomic_add_t(&C[n0 + tid], s_col[tid]);
     return;
   }
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t gi = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gi = m0 + rowi(i);
     if (gi >= m) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int64_t gj = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+    for (int j = 0; j < TN; ++j) {
+      const int64_t gj = n0 + coli(j);
       if (gj >= n) continue;
       T* dst = C + gi * ldc + gj;
       const T v = alpha * acc[i][j];
@@ -327,7 +340,7 @@ gemm_simt_kernel(int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t l
     if (tid == 0) {
       __threadfence();
       atomicAdd(head_flag, 1);
-      const int u = diag_units_tile(m0, n0, GB, GB, m, n);
+      const int u = diag_units_tile(m0, n0, BM, BN, m, n);
       if (u) atomicAdd(head_flag + 1, u);
     }
   }
@@ -387,21 +400,43 @@ gemm_skinny_kernel(int64_t m, int n, int64_t k, T alpha, const T* A, int64_t lda
       *dst = beta != T(0) ? alpha * s + beta * *dst : alpha * s;
     }
   } else {
-    // A stored [k][m]: one thread per output row, coalesced across threads
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    for (int64_t kk = 0; kk < k; ++kk) {
-      const T a = A[kk * lda + i];
-      const T* brow = B + kk * ldb;
+    // A stored [k][m]: a CTA covers 32 output rows (lanes -> consecutive rows: coalesced), its 8 warps split k with
+    // 4 loads in flight per lane; partial sums meet in shared memory.  (One thread per row over the whole k was
+    // latency-bound: 1.0 ms for the SVGP mean A^T q_mu at M = 2048, B = 4096.)
+    __shared__ T red[8][32][SKN + 1];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    const int64_t kchunk = (k + 7) / 8, k0 = wp * kchunk, k1 = min(k, k0 + kchunk);
+    if (i < m) {
+      int64_t kk = k0;
+      for (; kk + 3 < k1; kk += 4) {
+        const T a0 = A[kk * lda + i], a1 = A[(kk + 1) * lda + i], a2 = A[(kk + 2) * lda + i], a3 = A[(kk + 3) * lda + i];
 #pragma unroll
-      for (int j = 0; j < SKN; ++j)
-        if (j < n) acc[j] = fma(a, brow[j], acc[j]);
+        for (int j = 0; j < SKN; ++j)
+          if (j < n) {
+            acc[j] = fma(a0, B[kk * ldb + j], acc[j]);
+            acc[j] = fma(a1, B[(kk + 1) * ldb + j], acc[j]);
+            acc[j] = fma(a2, B[(kk + 2) * ldb + j], acc[j]);
+            acc[j] = fma(a3, B[(kk + 3) * ldb + j], acc[j]);
+          }
+      }
+      for (; kk < k1; ++kk) {
+        const T a = A[kk * lda + i];
+#pragma unroll
+        for (int j = 0; j < SKN; ++j)
+          if (j < n) acc[j] = fma(a, B[kk * ldb + j], acc[j]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < SKN; ++j)
-      if (j < n) {
+    for (int j = 0; j < SKN; ++j) red[wp][lane][j] = acc[j];
+    __syncthreads();
+    if (i < m)
+      for (int j = wp; j < n; j += 8) {
+        T sum = T(0);
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][lane][j];
         T* dst = C + i * ldc + j;
-        *dst = beta != T(0) ? alpha * acc[j] + beta * *dst : alpha * acc[j];
+        *dst = beta != T(0) ? alpha * sum + beta * *dst : alpha * sum;
       }
   }
 }
@@ -412,7 +447,7 @@ static int launch_skinny(int ta, int64_t m, int n, int64_t k, T alpha, const T* 
   if (!ta)
     gemm_skinny_kernel<T, false><<<(unsigned)m, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   else
-    gemm_skinny_kernel<T, true><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    gemm_skinny_kernel<T, true><<<(unsigned)((m + 31) / 32), 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   GPK_LAUNCH_OK();
   return 0;
 }
@@ -426,15 +461,40 @@ static bool fp64_simt() {
   return v == 1;
 }
 
-template <typename T>
-static int launch_simt(int ta, int tb, dim3 grid, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
-                       const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st, int* hf) {
-#define GO(TA_, TB_) gemm_simt_kernel<T, TA_, TB_><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
+template <typename T, int BM, int BN>
+static int launch_simt_shape(int ta, int tb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
+                             const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st, int* hf) {
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+  if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
+  GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
+#define GO(TA_, TB_) gemm_simt_kernel<T, TA_, TB_, BM, BN><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, hf)
   if (!ta && !tb) GO(false, false); else if (!ta && tb) GO(false, true);
   else if (ta && !tb) GO(true, false); else GO(true, true);
 #undef GO
   GPK_LAUNCH_OK();
   return 0;
+}
+
+// shape selection, same rules as launch_dmma: 128x128 when there are enough tiles to fill the machine, otherwise
+// narrower tiles; C aliasing A needs one tile across n (BN >= n), C aliasing B one tile across m
+template <typename T>
+static int launch_simt(int ta, int tb, int64_t m, int64_t n, int64_t k, T alpha, const T* A, int64_t lda,
+                       const T* B, int64_t ldb, T beta, T* C, int64_t ldc, int flags, cudaStream_t st, int* hf) {
+  const bool alias_a = (const void*)C == (const void*)A, alias_b = (const void*)C == (const void*)B;
+  const int64_t t128 = ((m + 127) / 128) * ((n + 127) / 128);
+#define SHAPE(BM_, BN_) return launch_simt_shape<T, BM_, BN_>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf)
+  if (t128 >= 120 || (flags & GPK_GEMM_COLSUMSQ)) SHAPE(128, 128);
+  if (alias_b || (m <= 128 && !alias_a)) {          // short and wide: split the columns finer
+    if ((n + 63) / 64 >= 100) SHAPE(128, 64);
+    SHAPE(128, 32);
+  }
+  if (alias_a || n <= 128) {                        // tall and narrow: split the rows finer
+    if ((m + 63) / 64 >= 100) SHAPE(64, 128);
+    SHAPE(32, 128);
+  }
+  if (((m + 63) / 64) * ((n + 127) / 128) >= 100) SHAPE(64, 128);
+  SHAPE(32, 128);
+#undef SHAPE
 }
 
 template <int BM, int BN>
@@ -503,10 +563,7 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
   if (sizeof(T) == 8 && !fp64_simt())
     return launch_dmma(transa, transb, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
                        (double)beta, (double*)C, ldc, flags, st, hf);
-  dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB));
-  if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
-  GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
-  return launch_simt<T>(transa, transb, grid, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf);
+  return launch_simt<T>(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st, hf);
 }
 
 template int gemm_t<float>(int, int, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t,
