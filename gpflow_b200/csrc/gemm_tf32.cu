@@ -136,9 +136,23 @@ constexpr int TF_KP = 64;                       // k elements per TMEM accumulat
 constexpr int TF_SPP = TF_KP / TF_KS;           // pipeline stages per run (4)
 constexpr int TF_THREADS = 320;                 // warp 0 producer, warp 1 MMA, warps 2..9 promotion/epilogue
 
+// Stage range [kb0, kb1) of k-split `ks` of row tile `tm`.  tri = 1: op(A) is lower triangular (k <= row), tri = 2:
+// upper triangular (k >= row, e.g. tril(q_sqrt)^T): the all-zero part of the K range is skipped (whole runs), which
+// halves the P batched products  tril(q_sqrt_p)^T A  of the SVGP conditional (conditionals/util.py:151-157).
+__device__ __forceinline__ void tf_krange(int tri, int64_t tm, int KB, int nsplit, int ks, int& kb0, int& kb1) {
+  int lo = 0, hi = KB;
+  if (tri == 2) lo = (int)((tm * TF_BM / TF_KS) / TF_SPP * TF_SPP);
+  if (tri == 1) { const int64_t e = ((tm + 1) * TF_BM + TF_KS - 1) / TF_KS; if (e < hi) hi = (int)e; }
+  if (lo > hi) lo = hi;
+  const int per = ((hi - lo + nsplit - 1) / nsplit + TF_SPP - 1) / TF_SPP * TF_SPP;  // whole runs per split
+  kb0 = lo + ks * per;
+  kb1 = kb0 + per < hi ? kb0 + per : hi;
+  if (kb0 > kb1) kb0 = kb1;
+}
+
 __global__ void __launch_bounds__(TF_THREADS, 1)
 gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Btiles, float* C, int64_t ldc, int64_t m,
-                 int64_t n, int KB, int nsplit, float alpha, float beta, int flags, int* err) {
+                 int64_t n, int KB, int nsplit, float alpha, float beta, int flags, int tri, int* err) {
   extern __shared__ __align__(1024) uint8_t tf_smem[];
   uint8_t* epi = tf_smem + TF_STAGES * TF_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 2 * TF_EPI_BYTES);  // full[4], empty[4], tfull[2], tempty[2]
@@ -158,14 +172,14 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int kb_per = ((KB + nsplit - 1) / nsplit + TF_SPP - 1) / TF_SPP * TF_SPP;  // whole runs per split
 
   if (warp == 0) {
     // ===== producer =====
     TfWork w(m, n, nsplit, lower);
     uint32_t st = 0, ph = 0;
     while (w.next()) {
-      const int kb0 = w.ks * kb_per, kb1 = min(KB, kb0 + kb_per);
+      int kb0, kb1;
+      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
       const char* a_src = reinterpret_cast<const char*>(Atiles) + (size_t)w.tm * KB * 2 * TF_APLANE;
       const char* b_src = reinterpret_cast<const char*>(Btiles) + (size_t)w.tn * KB * 2 * TF_BPLANE;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -187,7 +201,8 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     uint32_t st = 0, ph = 0, buf = 0, tph0 = 0, tph1 = 0;
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     while (w.next()) {
-      const int kb0 = w.ks * kb_per, kb1 = min(KB, kb0 + kb_per);
+      int kb0, kb1;
+      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
       for (int kr = kb0; kr < kb1; kr += TF_SPP) {
         mbar_wait(tempty0 + 8 * buf, (buf ? tph1 : tph0) ^ 1, err, 202);
         tc_fence_after();
@@ -228,7 +243,8 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     TfWork w(m, n, nsplit, lower);
     uint32_t buf = 0, tph0 = 0, tph1 = 0;
     while (w.next()) {
-      const int kb0 = w.ks * kb_per, kb1 = min(KB, kb0 + kb_per);
+      int kb0, kb1;
+      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
       float acc[128];
 #pragma unroll
       for (int c = 0; c < 128; ++c) acc[c] = 0.f;
@@ -403,7 +419,8 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   }
   int grid = (int)std::min<int64_t>(sms, ntiles * nsplit);
   ProfScope ps(PROF_GEMM, st);
-  gemm_tf32_kernel<<<grid, TF_THREADS, smem, st>>>(At, Bt, C, ldc, m, n, (int)KB, nsplit, alpha, beta, flags, err);
+  const int tri = (flags & GPK_GEMM_A_LOWER) ? (transa ? 2 : 1) : 0;
+  gemm_tf32_kernel<<<grid, TF_THREADS, smem, st>>>(At, Bt, C, ldc, m, n, (int)KB, nsplit, alpha, beta, flags, tri, err);
   GPK_LAUNCH_OK();
   return 0;
 }
