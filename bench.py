@@ -229,10 +229,20 @@ class OurArm:
             Yd = pinned["Y"].to(dev, non_blocking=True)
             h2d = pinned["X"].numel() * pinned["X"].element_size() + pinned["Y"].numel() * pinned["Y"].element_size()
             if name == "gpr_c5":
+                # independent outputs: one stream per output (as in eval_resident), workspaces of the resident models
+                if not hasattr(self, "_streams"):
+                    self._streams = [T.cuda.Stream() for _ in self.models]
+                cur = T.cuda.current_stream()
+                vals = []
+                for p, (m0, s_) in enumerate(zip(self.models, self._streams)):
+                    s_.wait_stream(cur)
+                    with T.cuda.stream(s_):
+                        m = gpf.models.GPR((Xd, Yd[:, p:p + 1].contiguous()), m0.kernel, noise_variance=0.1)
+                        m._ws, m._out = m0._ws, m0._out
+                        vals.append(m.log_marginal_likelihood().reshape(1).clone())
+                for s_ in self._streams:
+                    cur.wait_stream(s_)
                 tot = 0.0
-                ms = [gpf.models.GPR((Xd, Yd[:, p:p + 1].contiguous()), make_kernel(name, K, hp["D"], p), noise_variance=0.1)
-                      for p in range(hp["P"])]
-                vals = [m.log_marginal_likelihood().reshape(1).clone() for m in ms]
                 for v in vals:
                     tot += float(v.item())
                 return tot, h2d, 8 * hp["P"]

@@ -99,29 +99,35 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
 constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TF_BN >> 3) << 17) |
                               ((uint32_t)(TF_BM >> 4) << 24);
 
-struct TfWork {  // work item = (row tile, column tile, k split), identical enumeration in every role
+struct TfWork {  // work unit = (CL vertically adjacent row tiles, column tile, k split); same enumeration in every role
   int64_t ntm, ntn;
-  int nsplit, lower;
-  int64_t idx, tm, tn;
+  int nsplit, lower, cl, rank;
+  int64_t idx, tm0, tm, tn;  // tm0 = first row tile of the unit, tm = this CTA's row tile (tm0 + rank)
   int ks;
-  __device__ TfWork(int64_t m, int64_t n, int nsplit_, int lower_) : nsplit(nsplit_), lower(lower_), idx(-1), tm(0), tn(0), ks(-1) {
+  __device__ TfWork(int64_t m, int64_t n, int nsplit_, int lower_, int cl_, int rank_)
+      : nsplit(nsplit_), lower(lower_), cl(cl_), rank(rank_), idx(-1), tm0(0), tm(0), tn(0), ks(-1) {
     ntm = (m + TF_BM - 1) / TF_BM;
     ntn = (n + TF_BN - 1) / TF_BN;
   }
-  __device__ bool skip() const { return lower && tn * TF_BN > tm * TF_BM + TF_BM - 1; }
-  // Order: k-splits innermost, then ROW tiles, column tiles outermost: the (large) B tile of a column
+  __device__ bool tile_skip(int64_t t) const { return lower && tn * TF_BN > t * TF_BM + TF_BM - 1; }
+  __device__ bool unit_skip() const { return tile_skip(tm0 + cl - 1); }  // the lowest tile of the unit decides
+  // this CTA's tile takes part in the loads / MMAs of its unit but is not stored when it is padding
+  __device__ bool valid() const { return tm < ntm && !tile_skip(tm); }
+  __device__ int64_t tm_load() const { return tm < ntm ? tm : ntm - 1; }
+  // Order: k-splits innermost, then ROW units, column tiles outermost: the (large) B tile of a column
   // block is reused by consecutive work items while it is still in L2 (measured before: 4.5x re-reads
   // of the B planes from HBM with column tiles innermost).
   __device__ bool next() {
+    const int64_t nclusters = gridDim.x / cl, my = blockIdx.x / cl;
     for (;;) {
       ++ks;
-      if (ks >= nsplit) { ks = 0; ++tm; }
-      while (tn < ntn && (tm >= ntm || skip())) {
-        if (tm >= ntm) { tm = 0; ++tn; } else { ++tm; }
+      if (ks >= nsplit) { ks = 0; tm0 += cl; }
+      while (tn < ntn && (tm0 >= ntm || unit_skip())) {
+        if (tm0 >= ntm) { tm0 = 0; ++tn; } else { tm0 += cl; }
       }
       if (tn >= ntn) return false;
       ++idx;
-      if (idx % gridDim.x == blockIdx.x) return true;
+      if (idx % nclusters == my) { tm = tm0 + rank; return true; }
     }
   }
 };
@@ -139,10 +145,11 @@ constexpr int TF_THREADS = 320;                 // warp 0 producer, warp 1 MMA, 
 // Stage range [kb0, kb1) of k-split `ks` of row tile `tm`.  tri = 1: op(A) is lower triangular (k <= row), tri = 2:
 // upper triangular (k >= row, e.g. tril(q_sqrt)^T): the all-zero part of the K range is skipped (whole runs), which
 // halves the P batched products  tril(q_sqrt_p)^T A  of the SVGP conditional (conditionals/util.py:151-157).
-__device__ __forceinline__ void tf_krange(int tri, int64_t tm, int KB, int nsplit, int ks, int& kb0, int& kb1) {
+__device__ __forceinline__ void tf_krange(int tri, int64_t tm_first, int64_t tm_last, int KB, int nsplit, int ks, int& kb0,
+                                          int& kb1) {  // common range of the row tiles tm_first..tm_last of one unit
   int lo = 0, hi = KB;
-  if (tri == 2) lo = (int)((tm * TF_BM / TF_KS) / TF_SPP * TF_SPP);
-  if (tri == 1) { const int64_t e = ((tm + 1) * TF_BM + TF_KS - 1) / TF_KS; if (e < hi) hi = (int)e; }
+  if (tri == 2) lo = (int)((tm_first * TF_BM / TF_KS) / TF_SPP * TF_SPP);
+  if (tri == 1) { const int64_t e = ((tm_last + 1) * TF_BM + TF_KS - 1) / TF_KS; if (e < hi) hi = (int)e; }
   if (lo > hi) lo = hi;
   const int per = ((hi - lo + nsplit - 1) / nsplit + TF_SPP - 1) / TF_SPP * TF_SPP;  // whole runs per split
   kb0 = lo + ks * per;
@@ -150,6 +157,9 @@ __device__ __forceinline__ void tf_krange(int tri, int64_t tm, int KB, int nspli
   if (kb0 > kb1) kb0 = kb1;
 }
 
+// CL = 2: the two CTAs of a cluster work on vertically adjacent row tiles of the same column tile and share the B
+// planes (each fetches half of every plane and multicasts it): 48 -> 32 KB of L2->SM traffic per stage per CTA.
+template <int CL>
 __global__ void __launch_bounds__(TF_THREADS, 1)
 gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Btiles, float* C, int64_t ldc, int64_t m,
                  int64_t n, int KB, int nsplit, float alpha, float beta, int flags, int tri, int* err) {
@@ -163,24 +173,27 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
   const int lower = (flags & GPK_GEMM_LOWER_ONLY) ? 1 : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TF_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < TF_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers initialised before any multicast copy / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     // ===== producer =====
-    TfWork w(m, n, nsplit, lower);
+    TfWork w(m, n, nsplit, lower, CL, rank);
     uint32_t st = 0, ph = 0;
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
-      const char* a_src = reinterpret_cast<const char*>(Atiles) + (size_t)w.tm * KB * 2 * TF_APLANE;
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
+      const char* a_src = reinterpret_cast<const char*>(Atiles) + (size_t)w.tm_load() * KB * 2 * TF_APLANE;
       const char* b_src = reinterpret_cast<const char*>(Btiles) + (size_t)w.tn * KB * 2 * TF_BPLANE;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty0 + 8 * st, ph ^ 1, err, 201);
@@ -189,7 +202,15 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
           mbar_expect_tx(fb, TF_STAGE_BYTES);
           const uint32_t sa = smem_u32(tf_smem + (size_t)st * TF_STAGE_BYTES);
           bulk_g2s(sa, a_src + (size_t)kb * 2 * TF_APLANE, 2 * TF_APLANE, fb);
-          bulk_g2s(sa + 2 * TF_APLANE, b_src + (size_t)kb * 2 * TF_BPLANE, 2 * TF_BPLANE, fb);
+          if (CL == 1) {
+            bulk_g2s(sa + 2 * TF_APLANE, b_src + (size_t)kb * 2 * TF_BPLANE, 2 * TF_BPLANE, fb);
+          } else {
+            constexpr uint32_t part = TF_BPLANE / CL;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              bulk_g2s_mc(sa + 2 * TF_APLANE + pl * TF_BPLANE + rank * part,
+                          b_src + (size_t)kb * 2 * TF_BPLANE + pl * TF_BPLANE + rank * part, part, fb, cl_mask);
+          }
         }
         __syncwarp();
         if (++st == TF_STAGES) { st = 0; ph ^= 1; }
@@ -197,12 +218,12 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     }
   } else if (warp == 1) {
     // ===== MMA issuer: runs of TF_SPP stages into alternating TMEM buffers =====
-    TfWork w(m, n, nsplit, lower);
+    TfWork w(m, n, nsplit, lower, CL, rank);
     uint32_t st = 0, ph = 0, buf = 0, tph0 = 0, tph1 = 0;
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
       for (int kr = kb0; kr < kb1; kr += TF_SPP) {
         mbar_wait(tempty0 + 8 * buf, (buf ? tph1 : tph0) ^ 1, err, 202);
         tc_fence_after();
@@ -225,7 +246,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
               tc_mma_tf32(d, a_hi + o, b_lo + o, TF_IDESC, 1u);
               tc_mma_tf32(d, a_hi + o, b_hi + o, TF_IDESC, 1u);
             }
-            tc_commit(empty0 + 8 * st);
+            if (CL == 1) tc_commit(empty0 + 8 * st); else tc_commit_mc(empty0 + 8 * st, cl_mask);
           }
           __syncwarp();
           if (++st == TF_STAGES) { st = 0; ph ^= 1; }
@@ -240,11 +261,11 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     // ===== promotion + epilogue: 8 warps; warp (w-2): lane quarter q = w & 3, column half h = (w-2) >> 2 =====
     const int q = warp & 3, h = (warp - 2) >> 2;
     float* tile = reinterpret_cast<float*>(epi) + (warp - 2) * 32 * 33;
-    TfWork w(m, n, nsplit, lower);
+    TfWork w(m, n, nsplit, lower, CL, rank);
     uint32_t buf = 0, tph0 = 0, tph1 = 0;
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm, KB, nsplit, w.ks, kb0, kb1);
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
       float acc[128];
 #pragma unroll
       for (int c = 0; c < 128; ++c) acc[c] = 0.f;
@@ -269,7 +290,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int64_t col0 = w.tn * TF_BN + h * 128 + ch * 32;
-        if (col0 < n) {
+        if (col0 < n && w.valid()) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = alpha * acc[ch * 32 + c];
           __syncwarp();
@@ -308,6 +329,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -395,17 +417,18 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   }
   const int lower = (flags & GPK_GEMM_LOWER_ONLY) ? 1 : 0;
   const int64_t ntm = mpad / TF_BM, ntn = npad / TF_BN;
-  int64_t ntiles = 0;
-  for (int64_t tm = 0; tm < ntm; ++tm)
-    for (int64_t tn = 0; tn < ntn; ++tn)
-      if (!(lower && tn * TF_BN > tm * TF_BM + TF_BM - 1)) ++ntiles;
-  if (ntiles == 0) return 0;
+  // clusters of 2 row tiles share the B planes by multicast (GPK_TF32_CLUSTER=1 disables); a single row tile has no pair
+  static const int cl_env = []() { const char* e = getenv("GPK_TF32_CLUSTER"); return (e && e[0] == '1') ? 1 : 2; }();
+  const int cl = ntm >= 2 ? cl_env : 1;
+  int64_t nunits = 0;  // work units of cl vertically adjacent row tiles (the lowest tile decides whether a unit is needed)
+  for (int64_t tn = 0; tn < ntn; ++tn)
+    for (int64_t t0 = 0; t0 < ntm; t0 += cl)
+      if (!(lower && tn * TF_BN > (t0 + cl - 1) * TF_BM + TF_BM - 1)) ++nunits;
+  if (nunits == 0) return 0;
   const int sms = tf_num_sms();
   int nsplit = 1;
-  if (!(flags & GPK_GEMM_COLSUMSQ) || true) {
-    // split K when the tiles alone cannot fill the machine and K is deep
-    while (ntiles * nsplit < sms && KB / (nsplit * 2) >= 64 && nsplit < 64) nsplit *= 2;
-  }
+  // split K when the tiles alone cannot fill the machine and K is deep
+  while (nunits * cl * nsplit < sms && KB / (nsplit * 2) >= 64 && nsplit < 64) nsplit *= 2;
   if (nsplit > 1 && !(flags & GPK_GEMM_COLSUMSQ)) {
     scale_c_kernel<<<(unsigned)std::min<int64_t>((m * n + 255) / 256, 148 * 8), 256, 0, st>>>(C, ldc, m, n, beta);
     GPK_LAUNCH_OK();
@@ -414,14 +437,33 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   const size_t smem = (size_t)TF_STAGES * TF_STAGE_BYTES + 2 * TF_EPI_BYTES + 256;
   static bool attr = false;
   if (!attr) {
-    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = (int)std::min<int64_t>(sms, ntiles * nsplit);
-  ProfScope ps(PROF_GEMM, st);
+  int grid = (int)std::min<int64_t>(sms / cl * cl, nunits * cl * nsplit);
   const int tri = (flags & GPK_GEMM_A_LOWER) ? (transa ? 2 : 1) : 0;
-  gemm_tf32_kernel<<<grid, TF_THREADS, smem, st>>>(At, Bt, C, ldc, m, n, (int)KB, nsplit, alpha, beta, flags, tri, err);
-  GPK_LAUNCH_OK();
+  ProfScope ps(PROF_GEMM, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const float* Atc = At;
+  const float* Btc = Bt;
+  const int KBi = (int)KB;
+  if (cl == 2)
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<2>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err));
+  else
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<1>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err));
+  count_launch();
   return 0;
 }
 
