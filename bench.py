@@ -324,7 +324,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -505,13 +505,29 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout must carry exactly one JSON line: libraries (NCCL prints its version banner on stdout at some debug
+    # levels) get stderr instead -- file descriptor 1 is re-pointed at stderr and the original kept for emit()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
