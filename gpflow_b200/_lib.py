@@ -66,6 +66,8 @@ SIGNATURES = {
     "gpk_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "gpk_gaussian_varexp_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double, c_int,
                                         c_void_p, c_int, c_void_p]),
+    "gpk_gaussian_log_density": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_int,
+                                         c_void_p]),
     "gpk_launch_count": (c_int64, []),
     "gpk_launch_count_reset": (None, []),
     "gpk_debug_leaf": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -233,6 +233,12 @@ int gpk_gaussian_varexp_sum(const void* Fmu, const void* Fvar, const void* Y, in
   return varexp_impl(Fmu, Fvar, Y, B, P, P, P, 1, noise_variance, scale, accumulate, out, dtype, (cudaStream_t)stream);
 }
 
+int gpk_gaussian_log_density(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P,
+                             double noise_variance, void* out, int dtype, void* stream) {
+  GPK_DTYPE_OK("gaussian_log_density");
+  return logdensity_rows_impl(Fmu, Fvar, Y, B, P, noise_variance, out, dtype, (cudaStream_t)stream);
+}
+
 size_t gpk_gpr_lml_ws(int64_t N, int64_t P, int dtype) { return gpr_lml_ws(N, P, dtype); }
 
 int gpk_gpr_lml(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* X, int64_t N,

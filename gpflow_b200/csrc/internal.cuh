@@ -18,6 +18,8 @@ int reduce_wsq_impl(const void* w, const void* x, int64_t n, int64_t inc, double
                     cudaStream_t st);
 int tril_sumsq_impl(const void* A, int64_t n, int64_t lda, int64_t stride, int batch, double scale, int accumulate,
                     double* out, int dtype, cudaStream_t st);
+int logdensity_rows_impl(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P, double noise, void* out,
+                         int dtype, cudaStream_t st);
 int varexp_impl(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P, int64_t ldy, int64_t var_sb,
                 int64_t var_sp, double noise, double scale, int accumulate, double* out, int dtype, cudaStream_t st);
 int axpby_impl(int64_t m, int64_t n, double a, const void* X, int64_t ldx, double b, void* Y, int64_t ldy, int dtype,

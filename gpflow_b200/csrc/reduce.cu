@@ -239,6 +239,35 @@ int tril_sumsq_impl(const void* A, int64_t n, int64_t lda, int64_t stride, int b
   return 0;
 }
 
+// predictive log density per row: out[n] = sum_p -1/2 (log 2pi + log(Fvar + s2) + (y - mu)^2 / (Fvar + s2))
+// (gpflow/likelihoods/scalar_continuous.py:133-136 with logdensities.py:29-30); one thread per row
+template <typename T>
+__global__ void logdensity_rows_kernel(const T* __restrict__ Fmu, const T* __restrict__ Fvar, const T* __restrict__ Y,
+                                       int64_t B, int64_t P, double noise, T* __restrict__ out) {
+  const int64_t nrow = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (nrow >= B) return;
+  double acc = 0.0;
+  for (int64_t p = 0; p < P; ++p) {
+    const double var = (double)Fvar[nrow * P + p] + noise;
+    const double d = (double)Fmu[nrow * P + p] - (double)Y[nrow * P + p];
+    acc += -0.5 * (1.8378770664093453 + log(var) + d * d / var);
+  }
+  out[nrow] = (T)acc;
+}
+
+int logdensity_rows_impl(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P, double noise, void* out,
+                         int dtype, cudaStream_t st) {
+  GPK_CHECK_ARG(noise > 0.0, "predict_log_density: noise variance must be positive");
+  GPK_CHECK_ARG(Fmu && Fvar && Y && out, "predict_log_density: null argument");
+  if (B <= 0 || P <= 0) return 0;
+  const unsigned g = (unsigned)((B + 255) / 256);
+  GPK_DISPATCH(dtype,
+               (logdensity_rows_kernel<float><<<g, 256, 0, st>>>((const float*)Fmu, (const float*)Fvar, (const float*)Y, B, P, noise, (float*)out)),
+               (logdensity_rows_kernel<double><<<g, 256, 0, st>>>((const double*)Fmu, (const double*)Fvar, (const double*)Y, B, P, noise, (double*)out)));
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
 int varexp_impl(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P, int64_t ldy, int64_t var_sb,
                 int64_t var_sp, double noise, double scale, int accumulate, double* out, int dtype, cudaStream_t st) {
   GPK_CHECK_ARG(noise > 0.0, "variational expectations: noise variance must be positive");

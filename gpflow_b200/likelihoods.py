@@ -58,8 +58,6 @@ class Gaussian(ScalarLikelihood):
         ops.axpby(1.0, ones, 1.0, out)
         return Fmu, out
 
-    def predict_log_density(self, X, Fmu, Fvar, Y):  # scalar_continuous.py:133-136 -> [N] on host
-        mu, var = self.predict_mean_and_var(X, Fmu, Fvar)
-        mu_h, var_h = mu.cpu().numpy(), var.cpu().numpy()
-        Yh = ops.to_device(Y).cpu().numpy()
-        return np.sum(-0.5 * (math.log(2 * math.pi) + np.log(var_h) + np.square(mu_h - Yh) / var_h), axis=-1)
+    def predict_log_density(self, X, Fmu, Fvar, Y):  # scalar_continuous.py:133-136 -> device vector [N]
+        Fmu, Fvar, Y = ops.to_device(Fmu), ops.to_device(Fvar), ops.to_device(Y)
+        return ops.gaussian_log_density(Fmu, Fvar, Y, self._variance_value())

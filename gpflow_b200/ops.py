@@ -273,6 +273,15 @@ def transpose(A, out=None):
     return out
 
 
+def gaussian_log_density(Fmu, Fvar, Y, noise_variance: float):
+    """out[n] = sum_p log N(Y[n,p] | Fmu[n,p], Fvar[n,p] + noise_variance) -> device vector [B]."""
+    Bn, P = Fmu.shape
+    out = torch().empty((Bn,), dtype=Fmu.dtype, device=Fmu.device)
+    check(_lib.load().gpk_gaussian_log_density(_p(Fmu), _p(Fvar), _p(Y), Bn, P, float(noise_variance), _p(out),
+                                               dtype_code(Fmu), _stream()), "gpk_gaussian_log_density")
+    return out
+
+
 def gaussian_varexp_sum(Fmu, Fvar, Y, noise_variance: float, *, scale: float = 1.0, out=None,
                         accumulate: bool = False):
     Bn, P = Fmu.shape

@@ -176,6 +176,11 @@ GPK_API int gpk_gaussian_varexp_sum(const void* Fmu, const void* Fvar, const voi
                             double noise_variance, double scale, int accumulate, double* out,
                             int dtype, void* stream);
 
+/* predictive log density per row: out[n] = sum_p log N(Y[n,p] | Fmu[n,p], Fvar[n,p] + noise_variance), out [B] of the
+ * same dtype (gpflow/likelihoods/scalar_continuous.py:133-136, logdensities.py:29-30; models/model.py:332-343). */
+GPK_API int gpk_gaussian_log_density(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P,
+                             double noise_variance, void* out, int dtype, void* stream);
+
 /* ---- Fused objectives: one call per evaluation ------------------------------------------- */
 
 /* GPR.log_marginal_likelihood (gpflow/models/gpr.py:91-107): K-build(lower)+noise, Cholesky with

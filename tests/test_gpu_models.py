@@ -68,6 +68,13 @@ def test_c2_reduced_gpr_matern52_golden(cuda_device):
     assert_allclose(np.diagonal(to_np(vf)[0]), to_np(var)[:, 0], rtol=1e-8, atol=1e-10)  # test_model_predict.py:137-153
     my, vy = m.predict_y(d["Xnew"])
     assert_allclose(to_np(vy), to_np(var) + 0.1, rtol=1e-12)
+    # predictive log density on the device (models/model.py:332-343, scalar_continuous.py:133-136;
+    # the reference checks it by hand in tests/gpflow/models/test_model_predict.py:119-135)
+    Ynew = np.sin(d["Xnew"][:, :1]) + 0.05
+    lpd = m.predict_log_density((d["Xnew"], Ynew))
+    assert lpd.is_cuda and tuple(lpd.shape) == (32,)
+    mo1, vo1 = O.gpr_predict_f(d["X"], d["Y"], kernels_for(2, 8), 0.1, d["Xnew"])
+    assert_allclose(to_np(lpd), O.gaussian_predict_log_density(mo1, vo1, Ynew, 0.1), rtol=1e-9, atol=1e-11)
     with pytest.raises(NotImplementedError):
         m.predict_f(d["Xnew"], full_output_cov=True)
 
