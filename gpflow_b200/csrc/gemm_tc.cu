@@ -176,7 +176,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
-  if (warp == 0) {
+  if (__all_sync(0xffffffffu, warp == 0)) {  // vote: the role branch is warp-uniform and the compiler knows it
     // ===== producer (whole warp runs the loop; one elected lane issues the copies) =====
     TcTileIter it(m, n, lower, CL, rank);
     uint32_t st = 0, ph = 0;
@@ -209,7 +209,7 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
         if (++st == TC_STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (__all_sync(0xffffffffu, warp == 1)) {
     // ===== MMA issuer (uniform control flow, one elected lane issues) =====
     TcTileIter it(m, n, lower, CL, rank);
     uint32_t st = 0, ph = 0, tph = 0;

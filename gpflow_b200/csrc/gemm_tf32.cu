@@ -186,7 +186,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
-  if (warp == 0) {
+  if (__all_sync(0xffffffffu, warp == 0)) {  // vote: the role branch is warp-uniform and the compiler knows it
     // ===== producer =====
     TfWork w(m, n, nsplit, lower, CL, rank);
     uint32_t st = 0, ph = 0;
@@ -216,7 +216,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
         if (++st == TF_STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (__all_sync(0xffffffffu, warp == 1)) {
     // ===== MMA issuer: runs of TF_SPP stages into alternating TMEM buffers =====
     TfWork w(m, n, nsplit, lower, CL, rank);
     uint32_t st = 0, ph = 0, buf = 0, tph0 = 0, tph1 = 0;

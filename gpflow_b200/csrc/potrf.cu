@@ -335,7 +335,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
       }
       if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");  // the next diagonal block is up to date
     }
-    if (tid < 32) {
+    if (__all_sync(0xffffffffu, tid < 32)) {  // warp-uniform by construction: the vote tells the compiler so
       const int bad = warp_chol32<T>(S, t0, ldiag);
       if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + t0 + bad);
     }
@@ -364,7 +364,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
     }
   }
   GPK_DBG(7);
-  if (tid < 128) warp_inv32<T>(S, (tid >> 5) * 32);  // the four 32x32 diagonal inverses, one warp each
+  if (__all_sync(0xffffffffu, tid < 128)) warp_inv32<T>(S, (tid >> 5) * 32);  // the four 32x32 diagonal inverses, one warp each
   __syncthreads();
   invert_offdiag_128<T>(S, tmp, !SLIM);
   GPK_DBG(8);
@@ -493,7 +493,7 @@ trtri_diag_kernel(const T* __restrict__ L, int64_t ldl, int64_t n, T* __restrict
   __syncthreads();
   if (tid < NB) S[tid * LS + tid] = T(1) / S[tid * LS + tid];  // diagonal slot holds inv(L)_kk
   __syncthreads();
-  if (tid < 128) warp_inv32<T>(S, (tid >> 5) * 32);
+  if (__all_sync(0xffffffffu, tid < 128)) warp_inv32<T>(S, (tid >> 5) * 32);
   __syncthreads();
   invert_offdiag_128<T>(S, tmp);
   write_dinv<T>(S, dinv + (size_t)blockIdx.x * NB * NB);
