@@ -59,9 +59,12 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   for (int c = 0; c < 32; ++c) a[c] = c <= lane ? S[(jb + lane) * LS + jb + c] : T(0);
   int bad = 0;
   T my_inv = T(1), my_diag = T(1);
-  // Right-looking, fully unrolled: 10k cycles per 32x32 block on B200.  Tried and rejected (measured): 8-column
-  // blocking (10.0k, no change), left-looking columns with four split partial sums (13.6k), shared-memory column
-  // broadcast (18.4k).  The block is bound by the 1056 SHFL.32 + 528 DFMA issue of one warp, not by the pivot chain.
+#ifndef GPK_CHOL32_VARIANT
+#define GPK_CHOL32_VARIANT 0
+#endif
+#if GPK_CHOL32_VARIANT == 0
+  // Right-looking, fully unrolled.  Alternatives measured (scripts/chol32_variants.sh): 8-column blocking and
+  // left-looking columns with four split partial sums.
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     T d = __shfl_sync(0xffffffffu, a[k], k);
@@ -79,6 +82,67 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
         if (lane >= j) a[j] -= a[k] * ljk;
       }
   }
+#elif GPK_CHOL32_VARIANT == 1
+  // left-looking: corrections from columns < j-1 go into four independent partial sums, only the last one sits on
+  // the pivot chain; entries above the diagonal accumulate harmless garbage (never read or stored)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j >= 2) {
+      T p0 = T(0), p1 = T(0), p2 = T(0), p3 = T(0);
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < j - 1) {
+          const T ljk = __shfl_sync(0xffffffffu, a[k], j);
+          if ((k & 3) == 0) p0 = fma(a[k], ljk, p0);
+          else if ((k & 3) == 1) p1 = fma(a[k], ljk, p1);
+          else if ((k & 3) == 2) p2 = fma(a[k], ljk, p2);
+          else p3 = fma(a[k], ljk, p3);
+        }
+      a[j] -= (p0 + p1) + (p2 + p3);
+    }
+    if (j >= 1) a[j] = fma(-a[j - 1], __shfl_sync(0xffffffffu, a[j - 1], j), a[j]);
+    T d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > T(0))) {
+      if (bad == 0) bad = j + 1;
+      d = T(1);
+    }
+    const T inv = rsqrt_t<T>(d);
+    if (lane == j) { my_inv = inv; my_diag = d * inv; }
+    a[j] *= inv;
+  }
+#else
+  // blocked by 8 columns: inside a block each pivot updates only the block's remaining columns; the columns to the
+  // right receive the block's 8 rank-1 updates afterwards (same subtraction order: bit-identical to variant 0)
+#pragma unroll
+  for (int kb = 0; kb < 32; kb += 8) {
+#pragma unroll
+    for (int k = kb; k < kb + 8; ++k) {
+      T d = __shfl_sync(0xffffffffu, a[k], k);
+      if (!(d > T(0))) {
+        if (bad == 0) bad = k + 1;
+        d = T(1);
+      }
+      const T inv = rsqrt_t<T>(d);
+      if (lane == k) { my_inv = inv; my_diag = d * inv; }
+      a[k] *= inv;
+#pragma unroll
+      for (int j = kb; j < kb + 8; ++j)
+        if (j > k) {
+          const T ljk = __shfl_sync(0xffffffffu, a[k], j);
+          if (lane >= j) a[j] -= a[k] * ljk;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= kb + 8) {
+#pragma unroll
+        for (int k = kb; k < kb + 8; ++k) {
+          const T ljk = __shfl_sync(0xffffffffu, a[k], j);
+          if (lane >= j) a[j] -= a[k] * ljk;
+        }
+      }
+  }
+#endif
 #pragma unroll
   for (int c = 0; c < 32; ++c)
     if (c < lane) S[(jb + lane) * LS + jb + c] = a[c];

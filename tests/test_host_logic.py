@@ -171,3 +171,20 @@ def test_product_has_no_cpu_fallback():
                 src += open(os.path.join(root, f)).read()
     assert "oracle" not in src.replace("gp_oracle", "oracle") or "import oracle" not in src
     assert "from oracle" not in src and "import oracle" not in src
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract: exactly ONE JSON line on stdout (library banners must not leak into it)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "gpr_c1",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["higher_is_better"] is True
