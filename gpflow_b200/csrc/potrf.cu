@@ -60,7 +60,7 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   int bad = 0;
   T my_inv = T(1), my_diag = T(1);
 #ifndef GPK_CHOL32_VARIANT
-#define GPK_CHOL32_VARIANT 0
+#define GPK_CHOL32_VARIANT 1  // measured on B200: 8.6k cycles per block (variant 0: 9.4k, variant 2: 9.8k)
 #endif
 #if GPK_CHOL32_VARIANT == 0
   // Right-looking, fully unrolled.  Alternatives measured (scripts/chol32_variants.sh): 8-column blocking and

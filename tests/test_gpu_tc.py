@@ -101,6 +101,10 @@ def test_gemm_tf32_flags(cuda_device):
         ref = np.tril(Q).T.astype(np.float64) @ Bm.astype(np.float64)
         got = ops.gemm(ops.to_device(Q), ops.to_device(Bm), transa=True, flags=_lib.GPK_GEMM_A_LOWER)
         assert np.all(np.abs(to_np(got) - ref) < 2e-6 * np.abs(ref) + 2e-4)
+        # lower-triangular A used untransposed: the K range ABOVE each row tile is skipped (tri = 1)
+        ref1 = np.tril(Q).astype(np.float64) @ Bm.astype(np.float64)
+        got1 = ops.gemm(ops.to_device(Q), ops.to_device(Bm), flags=_lib.GPK_GEMM_A_LOWER)
+        assert np.all(np.abs(to_np(got1) - ref1) < 2e-6 * np.abs(ref1) + 2e-4)
         v = ops.full((n,), 1.5, dtype=np.float32)
         ops.gemm(ops.to_device(Q), ops.to_device(Bm), transa=True, out=v,
                  flags=_lib.GPK_GEMM_A_LOWER | _lib.GPK_GEMM_COLSUMSQ)
