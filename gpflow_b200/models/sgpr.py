@@ -100,6 +100,43 @@ class SGPR(GPModel, InternalDataTrainingLossMixin):
         LB, _ = ops.cholesky(B)
         return self.CommonTensors(sigma_sq, sigma, A, B, LB, AAT, L)
 
+    def upper_bound(self):
+        """sgpr.py:87-147: Titsias' (2014) upper bound on the GPR log marginal likelihood, built from the individual
+        operators; device fp64 scalar.  (Scalar noise variance: L^-1 (Kuf / s) = (L^-1 Kuf) / s column-wise, so the
+        reference's three triangular solves share one.)"""
+        X, Y = self.data
+        N, P = Y.shape
+        s2 = self.likelihood._variance_value()
+        iv = self.inducing_variable
+        kdiag = self.kernel(X, full_cov=False)
+        kuu = covariances.Kuu(iv, self.kernel, jitter=config.default_jitter())
+        kuf = covariances.Kuf(iv, self.kernel, X)
+        M = kuu.shape[0]
+        L, dinv = ops.cholesky(kuu)
+        A = ops.trsm(L, kuf, dinv=dinv)                                                   # :118
+        # trace bound c = sum Kdiag - sum A^2 (:126): a scalar that enters cn_std = sqrt(s2 + c) below
+        c_dev = ops.reduce(ops.SUM, kdiag, N)
+        ops.reduce(ops.SUM, ops.colsumsq(A), N, scale=-1.0, out=c_dev, accumulate=True)
+        c = float(c_dev.item())
+        cn_std = (s2 + c) ** 0.5                                                           # :129-130
+        acc = ops.zeros_scalar(1)
+        B = ops.gemm(A, A, transb=True, alpha=1.0 / s2)                                   # AAT_sigma (:121)
+        ops.add_diag_(B, 1.0)
+        LB, _ = ops.cholesky(B)                                                            # :123
+        ops.reduce(ops.SUMLOG, LB, M, ops._ld(LB) + 1, scale=-1.0, out=acc, accumulate=True)   # logdet (:133)
+        Bc = ops.gemm(A, A, transb=True, alpha=1.0 / (cn_std * cn_std))                    # AAT_cn (:136)
+        ops.add_diag_(Bc, 1.0)
+        LC, dinvC = ops.cholesky(Bc)                                                       # :139
+        err = Y if isinstance(self.mean_function, Zero) else ops.axpby(-1.0, self.mean_function(X), 1.0, ops.copy(Y))
+        v = ops.gemm(A, err, alpha=1.0 / (cn_std * cn_std))                                # A_cn (err / cn_std) (:141)
+        ops.trsm(LC, v, dinv=dinvC)
+        ops.reduce(ops.SUMSQ, err, N * P, 1, scale=-0.5 / (cn_std * cn_std), out=acc, accumulate=True)   # :143
+        ops.reduce(ops.SUMSQ, v, M * P, 1, scale=0.5, out=acc, accumulate=True)
+        import math
+        const = -0.5 * N * math.log(2.0 * math.pi * s2)                                    # :132
+        ops.axpby(1.0, ops.full((1,), const, dtype="float64"), 1.0, acc)
+        return acc[0]
+
     def compute_qu(self) -> Tuple[Any, Any]:
         """sgpr.py:346-377: mean [M, P] and covariance [M, M] of q(u)."""
         X, Y = self.data

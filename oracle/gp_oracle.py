@@ -447,6 +447,34 @@ def sgpr_elbo(X, Y, kernel, Z, noise_variance, mean_function=None, jitter=DEFAUL
     return float(const + logdet + quad)
 
 
+def sgpr_upper_bound(X, Y, kernel, Z, noise_variance, mean_function=None, jitter=DEFAULT_JITTER) -> float:
+    """gpflow/models/sgpr.py:87-147 (Titsias 2014 upper bound on the GPR marginal likelihood; the reference checks
+    elbo < GPR lml < upper_bound in tests/integration/test_method_equivalence.py:297-327)."""
+    N, P = Y.shape
+    sigma_sq = np.broadcast_to(np.asarray(noise_variance, dtype=X.dtype), (N,)).copy()
+    sigma = np.sqrt(sigma_sq)
+    Kdiag = kernel(X, full_cov=False)
+    kuu = Kuu(Z, kernel, jitter=jitter)
+    kuf = Kuf(Z, kernel, X)
+    I = np.eye(kuu.shape[0], dtype=X.dtype)
+    L = cholesky(kuu)
+    A = tri_solve(L, kuf)
+    A_sigma = tri_solve(L, kuf / sigma)
+    B = I + A_sigma @ A_sigma.T
+    LB = cholesky(B)
+    c = np.sum(Kdiag) - np.sum(np.square(A))        # trace bound, sgpr.py:126
+    cn_var = sigma_sq + c
+    cn_std = np.sqrt(cn_var)
+    const = -0.5 * np.sum(np.log(2 * np.pi * sigma_sq))
+    logdet = -np.sum(np.log(np.diag(LB)))
+    A_cn = tri_solve(L, kuf / cn_std)
+    err = Y - _mean(mean_function, X, P)
+    LC = cholesky(I + A_cn @ A_cn.T)
+    v = tri_solve(LC, A_cn @ (err / cn_std[:, None]))
+    quad = -0.5 * np.sum(np.square(err / cn_std[:, None])) + 0.5 * np.sum(np.square(v))
+    return float(const + logdet + quad)
+
+
 def sgpr_predict_f(X, Y, kernel, Z, noise_variance, Xnew, mean_function=None, full_cov=False,
                    jitter=DEFAULT_JITTER):
     """gpflow/posteriors.py:479-551 (SGPRPosterior)."""
@@ -647,3 +675,30 @@ def make_q(config_index: int, M: int, P: int, dtype=np.float64):
     q_mu = 0.1 * rng.standard_normal((M, P))
     q_sqrt = np.stack([np.tril(0.1 * rng.standard_normal((M, M))) + np.eye(M) for _ in range(P)])
     return q_mu.astype(dtype), q_sqrt.astype(dtype)
+
+
+# ----------------------------------------------------------------------------------------
+# VGP (sibling model on the same operators)
+# ----------------------------------------------------------------------------------------
+def vgp_elbo(X, Y, kernel, q_mu, q_sqrt, noise_variance, mean_function=None, jitter=DEFAULT_JITTER) -> float:
+    """gpflow/models/vgp.py:111-143 with a Gaussian likelihood: whitened q(v) = N(q_mu, q_sqrt q_sqrt^T), f = L v + m."""
+    N, P = Y.shape
+    KL = gauss_kl(q_mu, q_sqrt)
+    K = kernel(X) + np.eye(N, dtype=X.dtype) * np.asarray(jitter, dtype=X.dtype)
+    L = cholesky(K)
+    fmean = L @ q_mu + _mean(mean_function, X, P)
+    q_sqrt_dnn = np.tril(q_sqrt)                       # band_part(q_sqrt, -1, 0)  [P, N, N]
+    LTA = np.matmul(L[None], q_sqrt_dnn)               # [P, N, N]
+    fvar = np.sum(np.square(LTA), axis=2).T            # [N, P]
+    var_exp = gaussian_variational_expectations(fmean, fvar, Y, noise_variance)
+    return float(np.sum(var_exp) - KL)
+
+
+def vgp_predict_f(X, kernel, q_mu, q_sqrt, Xnew, mean_function=None, full_cov=False, jitter=DEFAULT_JITTER):
+    """gpflow/models/vgp.py:145-161 -> conditionals/conditionals.py:39-116 (Kmm = K(X) + jitter I, white=True)."""
+    P = q_mu.shape[1]
+    Kmm = kernel(X) + np.eye(X.shape[0], dtype=X.dtype) * np.asarray(jitter, dtype=X.dtype)
+    Kmn = kernel(X, Xnew)
+    Knn = kernel(Xnew, full_cov=full_cov)
+    mean, var = base_conditional(Kmn, Kmm, Knn, q_mu, full_cov=full_cov, q_sqrt=q_sqrt, white=True)
+    return mean + _mean(mean_function, Xnew, P), var

@@ -171,6 +171,63 @@ def test_sgpr_multi_output_mean_function_full_cov(cuda_device):
     assert_allclose(to_np(common.LB), co.LB, rtol=1e-7, atol=1e-9)
 
 
+def test_sgpr_upper_bound_vs_oracle_and_brackets_gpr(cuda_device):
+    """SGPR.upper_bound (sgpr.py:87-147): parity with the oracle, and the reference's own check
+    elbo < GPR lml < upper_bound (tests/integration/test_method_equivalence.py:297-327) on its DatumUpper data."""
+    rng = np.random.default_rng(123)
+    X = rng.random((100, 1))
+    Y = np.sin(1.5 * 2 * np.pi * X) + rng.standard_normal(X.shape) * 0.1 + 5.3
+    Z = X[:10].copy()
+    ko, kp = O.SquaredExponential(variance=1.3, lengthscales=0.3), gpf.kernels.SquaredExponential(variance=1.3, lengthscales=0.3)
+    mf_o, mf_p = O.ConstantMean([5.0]), gpf.mean_functions.Constant([5.0])
+    m = gpf.models.SGPR((X, Y), kp, Z, mean_function=mf_p, noise_variance=0.05)
+    ub, elbo = float(m.upper_bound()), float(m.elbo())
+    assert_allclose(ub, O.sgpr_upper_bound(X, Y, ko, Z, 0.05, mf_o), rtol=1e-9)
+    lml = float(gpf.models.GPR((X, Y), kp, mean_function=mf_p, noise_variance=0.05).log_marginal_likelihood())
+    assert elbo < lml < ub
+    # two outputs, larger M (two diagonal blocks in each factorisation)
+    X2, Y2, Z2 = rng.standard_normal((400, 3)), rng.standard_normal((400, 2)), rng.standard_normal((150, 3))
+    ko2, kp2 = build("m32", 3, [O, gpf.kernels])
+    m2 = gpf.models.SGPR((X2, Y2), kp2, Z2, noise_variance=0.3)
+    assert_allclose(float(m2.upper_bound()), O.sgpr_upper_bound(X2, Y2, ko2, Z2, 0.3), rtol=1e-9)
+
+
+@pytest.mark.parametrize("N,P", [(60, 1), (200, 2)])
+def test_vgp_elbo_and_predict_vs_oracle(cuda_device, N, P):
+    """VGP with a Gaussian likelihood (vgp.py:111-161) against the oracle; with q set to the exact whitened posterior
+    the ELBO equals the GPR log marginal likelihood (the fixed point test_method_equivalence.py reaches by training)."""
+    rng = np.random.default_rng(N + P)
+    X, Xn = rng.standard_normal((N, 2)), rng.standard_normal((11, 2))
+    Y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, P))
+    ko, kp = build("m32", 2, [O, gpf.kernels])
+    q_mu = 0.3 * rng.standard_normal((N, P))
+    q_sqrt = np.stack([np.tril(0.1 * rng.standard_normal((N, N))) + np.eye(N) for _ in range(P)])
+    mf_o, mf_p = O.ConstantMean([0.2] * P), gpf.mean_functions.Constant([0.2] * P)
+    m = gpf.models.VGP((X, Y), kp, gpf.likelihoods.Gaussian(0.2), mean_function=mf_p)
+    m.q_mu.assign(q_mu)
+    m.q_sqrt.assign(q_sqrt)
+    assert_allclose(float(m.elbo()), O.vgp_elbo(X, Y, ko, q_mu, q_sqrt, 0.2, mf_o), rtol=1e-9)
+    assert_allclose(float(m.training_loss()), -float(m.elbo()), rtol=1e-12)
+    mean, var = m.predict_f(Xn)
+    mo, vo = O.vgp_predict_f(X, ko, q_mu, q_sqrt, Xn, mf_o)
+    assert_allclose(to_np(mean), mo, **F64)
+    assert_allclose(to_np(var), vo, **F64)
+    mf, vf = m.predict_f(Xn, full_cov=True)
+    mo2, vo2 = O.vgp_predict_f(X, ko, q_mu, q_sqrt, Xn, mf_o, full_cov=True)
+    assert_allclose(to_np(vf), vo2, rtol=1e-7, atol=1e-8)
+    if P == 1:  # exact posterior in whitened coordinates  =>  ELBO == GPR LML (jitter aside)
+        s2 = 0.2
+        K = ko(X) + 1e-6 * np.eye(N)
+        L = np.linalg.cholesky(K)
+        Ky = K + s2 * np.eye(N)
+        mu = K @ np.linalg.solve(Ky, Y - 0.2)
+        S = K - K @ np.linalg.solve(Ky, K)
+        m.q_mu.assign(np.linalg.solve(L, mu))
+        m.q_sqrt.assign(np.linalg.solve(L, np.linalg.cholesky(S + 1e-12 * np.eye(N)))[None])
+        lml = float(gpf.models.GPR((X, Y), kp, mean_function=mf_p, noise_variance=s2).log_marginal_likelihood())
+        assert_allclose(float(m.elbo()), lml, rtol=1e-5)
+
+
 def test_method_equivalence_on_device(cuda_device):
     """tests/integration/test_method_equivalence.py:181-241 at fixed hyper-parameters, on the GPU path."""
     rng = np.random.RandomState(0)

@@ -278,3 +278,47 @@ def test_log_density_by_hand():
     got = O.gaussian_predict_log_density(mu, var, Y, s2)
     want = scipy.stats.norm.logpdf(Y, loc=mu, scale=np.sqrt(var + s2)).sum(-1)
     assert_allclose(got, want)
+
+
+# ---- sibling models on the same operators ------------------------------------------------------
+def test_sgpr_upper_bound_brackets_the_marginal_likelihood():
+    """tests/integration/test_method_equivalence.py:297-327 (DatumUpper: rng 123, X rand(100,1), offset 5.3) at fixed
+    hyper-parameters: elbo < GPR lml < upper_bound."""
+    rng = np.random.default_rng(123)
+    X = rng.random((100, 1))
+    Y = np.sin(1.5 * 2 * np.pi * X) + rng.standard_normal(X.shape) * 0.1 + 5.3
+    assert Y.mean() > 5.0
+    k = O.SquaredExponential(variance=1.3, lengthscales=0.3)
+    mf = O.ConstantMean([5.0])
+    Z = X[:10].copy()
+    elbo = O.sgpr_elbo(X, Y, k, Z, 0.05, mf)
+    lml = O.gpr_log_marginal_likelihood(X, Y, k, 0.05, mf)
+    ub = O.sgpr_upper_bound(X, Y, k, Z, 0.05, mf)
+    assert elbo < lml < ub
+    # with Z = X both bounds are tight (the trace term vanishes)
+    assert abs(O.sgpr_upper_bound(X, Y, k, X.copy(), 0.05, mf, jitter=1e-10) - lml) < 1e-4 * abs(lml)
+
+
+def test_vgp_with_exact_posterior_equals_gpr():
+    """VGP (vgp.py:111-161) with q(v) set to the exact whitened posterior: ELBO == GPR log marginal likelihood and
+    the predictions coincide -- the fixed point the reference's method-equivalence test reaches by optimisation
+    (tests/integration/test_method_equivalence.py:181-241)."""
+    rng = np.random.default_rng(7)
+    N = 30
+    X = rng.standard_normal((N, 2))
+    Y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((N, 1))
+    k = O.Matern32(variance=0.9, lengthscales=1.1)
+    s2, jit = 0.2, 1e-10
+    K = k(X) + jit * np.eye(N)
+    L = np.linalg.cholesky(K)
+    Ky = K + s2 * np.eye(N)
+    mu = K @ np.linalg.solve(Ky, Y)
+    S = K - K @ np.linalg.solve(Ky, K)
+    q_mu = np.linalg.solve(L, mu)
+    q_sqrt = np.linalg.solve(L, np.linalg.cholesky(S + 1e-14 * np.eye(N)))[None]
+    assert abs(O.vgp_elbo(X, Y, k, q_mu, q_sqrt, s2, jitter=jit) - O.gpr_log_marginal_likelihood(X, Y, k, s2)) < 1e-6
+    Xn = rng.standard_normal((5, 2))
+    m1, v1 = O.vgp_predict_f(X, k, q_mu, q_sqrt, Xn, jitter=jit)
+    m2, v2 = O.gpr_predict_f(X, Y, k, s2, Xn)
+    np.testing.assert_allclose(m1, m2, atol=1e-8)
+    np.testing.assert_allclose(v1, v2, atol=1e-8)
