@@ -13,7 +13,7 @@ GPK_GEMM_LOWER_ONLY, GPK_GEMM_A_LOWER, GPK_GEMM_COLSUMSQ = 1, 2, 4
 GPK_MAX_CHILDREN = 8
 
 (K_RBF, K_MATERN12, K_MATERN32, K_MATERN52, K_RQ, K_EXPONENTIAL, K_LINEAR, K_WHITE, K_CONSTANT, K_SUM,
- K_PRODUCT) = range(11)
+ K_PRODUCT, K_POLYNOMIAL) = range(12)
 
 
 class KNode(ctypes.Structure):

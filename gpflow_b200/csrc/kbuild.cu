@@ -42,8 +42,9 @@ static_assert(sizeof(KProg) < 4000, "KProg must fit the kernel parameter space")
 // ---------------------------------------------------------------------------------------------
 // host: flatten the reference-shaped node list into groups / leaves / postfix ops
 // ---------------------------------------------------------------------------------------------
-static bool is_leaf_op(int op) { return op >= GPK_K_RBF && op <= GPK_K_CONSTANT; }
-static bool uses_gram(int op) { return op <= GPK_K_LINEAR; }
+static bool is_leaf_op(int op) { return (op >= GPK_K_RBF && op <= GPK_K_CONSTANT) || op == GPK_K_POLYNOMIAL; }
+static bool uses_gram(int op) { return op <= GPK_K_LINEAR || op == GPK_K_POLYNOMIAL; }
+static bool linear_like(int op) { return op == GPK_K_LINEAR || op == GPK_K_POLYNOMIAL; }  // variance weights on the A side
 
 static int emit_ops(const gpk_knode* nodes, int idx, const std::vector<int>& leaf_of, KProg& p, int& depth,
                     int& max_depth) {
@@ -77,7 +78,7 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
   int tot_dims = 0;
   for (int i = 0; i < n_nodes; ++i) {
     const gpk_knode& nd = nodes[i];
-    GPK_CHECK_ARG(nd.op >= GPK_K_RBF && nd.op <= GPK_K_PRODUCT, "kbuild: unknown kernel op %d", nd.op);
+    GPK_CHECK_ARG(nd.op >= GPK_K_RBF && nd.op <= GPK_K_POLYNOMIAL, "kbuild: unknown kernel op %d", nd.op);
     if (!is_leaf_op(nd.op)) continue;
     GPK_CHECK_ARG(p.n_leaves < KB_MAXL, "kbuild: more than %d leaf kernels", KB_MAXL);
     int l = p.n_leaves++;
@@ -85,7 +86,7 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
     p.l_type[l] = nd.op;
     p.l_var[l] = nd.variance;
     p.l_alpha[l] = nd.alpha;
-    p.l_scale[l] = 1.0;
+    p.l_scale[l] = nd.op == GPK_K_POLYNOMIAL ? nd.lengthscale : 1.0;  // Polynomial: the offset rides in this slot
     p.l_group[l] = -1;
     if (!uses_gram(nd.op)) continue;
     int nd_dims = nd.n_dims > 0 ? nd.n_dims : (int)D;
@@ -98,16 +99,16 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
       w.resize(nd_dims);
       for (int d = 0; d < nd_dims; ++d) {
         double a = ard[nd.ard_off + d];
-        w[d] = nd.op == GPK_K_LINEAR ? a : 1.0 / a;  // stationary: X/l on BOTH sides (stationaries.py:77-79)
+        w[d] = linear_like(nd.op) ? a : 1.0 / a;  // stationary: X/l on BOTH sides (stationaries.py:77-79)
       }
-      if (nd.op == GPK_K_LINEAR) p.l_var[l] = 1.0;
-    } else if (nd.op != GPK_K_LINEAR) {
+      if (linear_like(nd.op)) p.l_var[l] = 1.0;
+    } else if (!linear_like(nd.op)) {
       p.l_scale[l] = 1.0 / (nd.lengthscale * nd.lengthscale);
     }
     // find or create the group
     int g = -1;
     for (int c = 0; c < p.n_groups && g < 0; ++c) {
-      const int wmode = w.empty() ? 0 : (nd.op == GPK_K_LINEAR ? 1 : 2);
+      const int wmode = w.empty() ? 0 : (linear_like(nd.op) ? 1 : 2);
       if (p.g_ndims[c] != nd_dims || p.g_weighted[c] != wmode) continue;
       bool same = true;
       for (int d = 0; d < nd_dims && same; ++d) {
@@ -122,7 +123,7 @@ int compile_kprog(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
       g = p.n_groups++;
       p.g_ndims[g] = nd_dims;
       p.g_off[g] = tot_dims;
-      p.g_weighted[g] = w.empty() ? 0 : (nd.op == GPK_K_LINEAR ? 1 : 2);  // 1: A side only, 2: both sides
+      p.g_weighted[g] = w.empty() ? 0 : (linear_like(nd.op) ? 1 : 2);  // 1: A side only, 2: both sides
       for (int d = 0; d < nd_dims; ++d) {
         int col = nd.n_dims > 0 ? dims[nd.dims_off + d] : d;
         GPK_CHECK_ARG(col >= 0 && col < D, "kbuild: active dim %d out of range [0,%lld)", col, (long long)D);
@@ -163,6 +164,7 @@ template <typename T>
 __device__ __forceinline__ T leaf_value(int type, T dot, T na, T nb, T scale, T var, T alpha, bool on_diag) {
   using M = KMath<T>;
   if (type == GPK_K_LINEAR) return var * dot;
+  if (type == GPK_K_POLYNOMIAL) return M::pow_(var * dot + scale, alpha);  // linears.py:108 (offset rides in `scale`)
   if (type == GPK_K_CONSTANT) return var;
   if (type == GPK_K_WHITE) return on_diag ? var : T(0);
   T r2 = scale * (na + nb - T(2) * dot);  // ops.py:113-122 — may be slightly negative
@@ -349,7 +351,7 @@ __global__ void kdiag_kernel(const __grid_constant__ KProg prog, const T* __rest
     const int op = prog.ops[o];
     if (op < KB_MAXL) {
       T v = T(prog.l_var[op]);  // stationaries.py:82-83, statics.py:41-42
-      if (prog.l_type[op] == GPK_K_LINEAR) {  // linears.py:67-68
+      if (prog.l_type[op] == GPK_K_LINEAR || prog.l_type[op] == GPK_K_POLYNOMIAL) {  // linears.py:67-68, 111-112
         const int g = prog.l_group[op];
         T acc = T(0);
         for (int d = 0; d < prog.g_ndims[g]; ++d) {
@@ -357,6 +359,7 @@ __global__ void kdiag_kernel(const __grid_constant__ KProg prog, const T* __rest
           acc += T(prog.w[prog.g_off[g] + d]) * x * x;
         }
         v *= acc;
+        if (prog.l_type[op] == GPK_K_POLYNOMIAL) v = KMath<T>::pow_(v + T(prog.l_scale[op]), T(prog.l_alpha[op]));
       }
       s3 = s2; s2 = s1; s1 = s0; s0 = v;
     } else {

@@ -49,7 +49,8 @@ enum {
   GPK_K_WHITE = 7,    /* sigma^2 delta_ij iff X2 is NULL, else 0 statics.py:57-63 */
   GPK_K_CONSTANT = 8, /* sigma^2                                 statics.py:78-91 */
   GPK_K_SUM = 9,      /* add_n of children                       base.py:305-308 */
-  GPK_K_PRODUCT = 10  /* product of children                     base.py:311-314 */
+  GPK_K_PRODUCT = 10, /* product of children                     base.py:311-314 */
+  GPK_K_POLYNOMIAL = 11 /* ((x*sigma^2) . x' + offset)^degree: offset in `lengthscale`, degree in `alpha`  linears.py:71-112 */
 };
 
 #define GPK_MAX_CHILDREN 8

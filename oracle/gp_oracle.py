@@ -207,6 +207,20 @@ class Linear(Kernel):
         return np.sum(np.square(X) * np.asarray(self.variance, dtype=X.dtype), axis=-1)
 
 
+class Polynomial(Linear):
+    """gpflow/kernels/linears.py:71-112: (sigma^2 x.y + offset)^degree."""
+
+    def __init__(self, degree=3.0, variance=1.0, offset=1.0, active_dims=None):
+        super().__init__(variance, active_dims)
+        self.degree, self.offset = degree, offset
+
+    def K(self, X, X2=None):  # linears.py:107-108
+        return (super().K(X, X2) + np.asarray(self.offset, dtype=X.dtype)) ** np.asarray(self.degree, dtype=X.dtype)
+
+    def K_diag(self, X):  # linears.py:111-112
+        return (super().K_diag(X) + np.asarray(self.offset, dtype=X.dtype)) ** np.asarray(self.degree, dtype=X.dtype)
+
+
 class Combination(Kernel):
     """gpflow/kernels/base.py:223-302 — flattens same-class nesting; children see unsliced X."""
 

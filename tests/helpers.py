@@ -15,6 +15,8 @@ SPECS = {
     "exp": ("Exponential", dict(variance=0.9, lengthscales=1.1)),
     "lin": ("Linear", dict(variance=0.6)),
     "lin_ard": ("Linear", dict(variance="ard")),
+    "poly": ("Polynomial", dict(degree=3.0, variance=0.35, offset=0.8)),
+    "poly_ard": ("Polynomial", dict(degree=2.0, variance="ard", offset=1.3)),
     "const": ("Constant", dict(variance=0.4)),
     "white": ("White", dict(variance=0.3)),
 }

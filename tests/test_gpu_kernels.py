@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 EXPRS = {
     "rbf": "rbf", "rbf_ard": "rbf_ard", "m12": "m12", "m32": "m32", "m52": "m52", "rq": "rq", "exp": "exp",
-    "lin": "lin", "lin_ard": "lin_ard", "const": "const", "white": "white",
+    "lin": "lin", "lin_ard": "lin_ard", "const": "const", "white": "white", "poly": "poly", "poly_ard": "poly_ard",
+    "poly*rbf+white": ("sum", ("prod", ("poly_ard", [1, 2]), "rbf"), "white"),
     "rbf+white": ("sum", "rbf", "white"),
     "sum3": ("sum", "rbf", "m32", "lin"),
     "prod": ("prod", "m52", "lin"),

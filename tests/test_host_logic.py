@@ -188,3 +188,24 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["higher_is_better"] is True
+
+
+def test_kernel_expressions_pass_the_host_compile_path_without_gpu():
+    """Every leaf op (incl. Polynomial, whose offset / degree ride in the lengthscale / alpha fields) must get past the
+    C-ABI's argument and expression checks (status -1 -> ValueError); without a device the call then fails only at
+    the CUDA launch (status -2)."""
+    lib = _lib.load()
+    K = gpf.kernels
+    exprs = [K.Polynomial(3.0, 0.35, 0.8),
+             K.Polynomial(2.0, [0.5, 0.7], 1.3, active_dims=[1, 2]) * K.RBF() + K.White(0.3),
+             (K.RBF() + K.Matern32(lengthscales=2.0)) * K.Linear(0.5) + K.RationalQuadratic(alpha=0.7) + K.Constant(0.1)]
+    buf = (ctypes.c_double * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    for k in exprs:
+        nodes, n, dims, ard = gpf.kernels.compile_kernel(k, 4)
+        st = lib.gpk_kbuild(nodes, n, dims, ard, ptr, 4, 4, None, 4, 0, 4, ptr, 4, _lib.GPK_F64, 0, 0.0, None, None)
+        assert st in (0, -2), lib.gpk_last_error().decode()
+    bad = gpf.kernels.compile_kernel(K.Polynomial(), 4)
+    bad[0][0].op = 99
+    assert lib.gpk_kbuild(bad[0], bad[1], bad[2], bad[3], ptr, 4, 4, None, 4, 0, 4, ptr, 4, _lib.GPK_F64, 0, 0.0, None, None) == -1
+    assert b"unknown kernel op" in lib.gpk_last_error()
