@@ -451,11 +451,16 @@ def run_ours(args):
     ach = work["chol_flops"] / gemm_s / 1e12 if gemm_s > 0 else 0.0
     peak = pk["bf16_sustained"]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_dmma_kernel (Cholesky trailing update + inverse-based TRSM blocks)"
-        if hp["dtype"] == np.float64 else "gemm_simt_kernel",
+        "bound": "tensor", "kernel": "Cholesky GEMM class: syrk_i8_kernel (tcgen05 kind::i8, digit-sliced fp64 SYRK, K >= 512 "
+        "levels) + gemm_dmma_kernel + potrf_panel_kernel" if hp["dtype"] == np.float64
+        else "GEMM class: gemm_tf32_kernel (tcgen05 kind::tf32 x3) + gemm_simt_kernel",
         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
         "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "pipe": "fp64 DMMA mma.sync.m8n8k4 (tcgen05 has no f64 kind)" if hp["dtype"] == np.float64 else "fp32 FFMA",
+        "pipe": "tcgen05 int8 (28 digit MMAs per 32-deep fp64 k-step; tcgen05 has no f64 kind) above K = 512, fp64 DMMA "
+        "mma.sync.m8n8k4 below; achieved = ALGORITHMIC fp64 flops / class time" if hp["dtype"] == np.float64
+        else "tcgen05 kind::tf32 (3 MMAs per fp32 product) + fp32 FFMA for small shapes",
+        "ncu_tensor_pipe_active": {"syrk_i8_kernel": 0.518, "gemm_tf32_kernel": 0.535,
+                                   "source": "profiles/ncu/r1_syrk_v2_raw.csv, r1_tf32_v2_raw.csv (one launch each)"},
         "pipe_peak_tflops_nominal": 37.0 if hp["dtype"] == np.float64 else 74.0,
         "pipe_frac_nominal": ach / (37.0 if hp["dtype"] == np.float64 else 74.0),
         "algorithmic_flops_per_step": work["chol_flops"], "launches_per_step": prof["gemm"]["launches_per_step"],
@@ -465,12 +470,12 @@ def run_ours(args):
     kb_ach = work["kbuild_bytes_lower"] / kb_s / 1e9 if kb_s > 0 else 0.0
     kbuild = {"bound": "hbm", "achieved": kb_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kb_ach / pk["hbm_gbs"],
               "algorithmic_bytes_per_step": work["kbuild_bytes_lower"], "ms_per_step": prof["kbuild"]["ms_per_step"],
-              "note": "inside the LML: lower-triangle tiles only (GPK_LOWER); fp64 exp/sqrt make it fp64-pipe bound"}
+              "note": "inside the LML: lower-triangle tiles only (GPK_LOWER); fp64 exp/sqrt make it fp64-pipe / issue bound"}
     if kfull:
         fa = work["kbuild_bytes_full"] / (kfull * 1e-3) / 1e9
         kbuild["full_matrix"] = {"ms": kfull, "achieved": fa, "frac": fa / pk["hbm_gbs"],
                                  "algorithmic_bytes": work["kbuild_bytes_full"],
-                                 "note": "standalone kernel(X): lower tiles computed once, mirrored tile written through shared memory"}
+                                 "note": "standalone kernel(X): lower tiles computed once, mirrored tile stored straight from registers"}
 
     # CPU baseline on this box's host cores: bounded sample = full evaluations for ~10-30 s
     threads = os.cpu_count() or 1
