@@ -286,6 +286,18 @@ def cpu_eval(name: str, hp: dict, threads: int):
     """The oracle port of the reference's algorithm on the host cores (CPU arm / cpu_baseline)."""
     from oracle import fast_cpu, gp_oracle as O
 
+    # torchrun exports OMP_NUM_THREADS=1 to its children: give BLAS/LAPACK all the host threads back for this leg
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=threads)
+    except Exception:  # noqa: BLE001
+        import contextlib
+        limit = contextlib.nullcontext()
+    with limit:
+        return _cpu_eval(name, hp, threads, fast_cpu, O)
+
+
+def _cpu_eval(name, hp, threads, fast_cpu, O):
     if name in ("gpr_c2", "gpr_c1"):
         return fast_cpu.gpr_lml_threaded(hp["X"], hp["Y"], make_kernel(name, O, hp["D"]), 0.1, threads)
     if name == "gpr_c5":
