@@ -642,7 +642,9 @@ template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,
                            size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
   GemmOpts opts;
+  // int32 accumulators: 64 * 64 * K * S < 2^31 (tests/test_digit_slicing_model.py); deeper updates use DMMA
   const bool use_tc = sizeof(T) == 8 && tcws && tc_enabled() && K >= tc_min_k() && K % 32 == 0 && n <= m &&
+                      K * tc_slices() * 4096 < (1ll << 31) &&
                       tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices());
   if (la.enabled) {
     GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 2 * sizeof(int), st));
