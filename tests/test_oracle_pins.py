@@ -322,3 +322,100 @@ def test_vgp_with_exact_posterior_equals_gpr():
     m2, v2 = O.gpr_predict_f(X, Y, k, s2, Xn)
     np.testing.assert_allclose(m1, m2, atol=1e-8)
     np.testing.assert_allclose(v1, v2, atol=1e-8)
+
+
+# ---- further reference tests restated on the oracle (tests/gpflow/kernels/test_kernels.py) ----------------------
+def test_white_sym_differs_from_explicit_x2():
+    """test_kernels.py:365-376: White()(X) != White()(X, X) (statics.py:57-63)."""
+    X = np.random.RandomState(1).randn(10, 3)
+    k = O.White()
+    assert not np.allclose(k(X), k(X, X))
+    assert np.all(k(X, X) == 0.0) and np.allclose(k(X), np.eye(10))
+
+
+_SLICE_CLASSES = [O.SquaredExponential, O.RationalQuadratic, O.Exponential, O.Matern12, O.Matern32, O.Matern52,
+                  O.Constant, O.Linear, O.Polynomial]
+
+
+@pytest.mark.parametrize("cls", _SLICE_CLASSES)
+def test_slice_symmetric_and_asymmetric(cls):
+    """test_kernels.py:396-424: active_dims=[i] on X equals the same kernel on the sliced column, list and slice forms."""
+    rng = np.random.RandomState(1)
+    X, Z = rng.randn(20, 2), rng.randn(12, 2)
+    k1, k2, k3 = cls(active_dims=[0]), cls(active_dims=[1]), cls(active_dims=slice(0, 1))
+    assert np.allclose(k1(X), k3(X[:, :1])) and np.allclose(k2(X), k3(X[:, 1:]))
+    assert np.allclose(k1(X, Z), k3(X[:, :1], Z[:, :1])) and np.allclose(k2(X, Z), k3(X[:, 1:], Z[:, 1:]))
+
+
+def test_product_and_active_product():
+    """test_kernels.py:425-458."""
+    rng = np.random.RandomState(1)
+    X = rng.randn(30, 2)
+    a, b = O.Matern32(), O.Matern52(lengthscales=0.3)
+    assert np.allclose(a(X) * b(X), (O.Matern32() * O.Matern52(lengthscales=0.3))(X))
+    for N, D in ((30, 4), (10, 7)):
+        X = rng.randn(N, D)
+        dims, idx, ls = list(range(D)), int(rng.randint(0, D)), rng.uniform(1.0, 7.0, D)
+        k_rest = O.SquaredExponential(lengthscales=np.hstack([ls[:idx], ls[idx + 1:]]), active_dims=dims[:idx] + dims[idx + 1:])
+        k_one = O.SquaredExponential(lengthscales=ls[idx], active_dims=[idx])
+        k_all = O.SquaredExponential(lengthscales=ls, active_dims=dims)
+        assert np.allclose(k_all(X), (k_rest * k_one)(X))
+
+
+def test_kernel_call_diag_and_x2_errors():
+    """test_kernels.py:621-627: full_cov=False with an explicit X2 is a ValueError (base.py:203-204)."""
+    rng = np.random.RandomState(1)
+    X, X2 = rng.randn(4, 1), rng.randn(5, 1)
+    for k in (O.SquaredExponential(), O.Matern32() + O.White(), O.Linear() * O.Constant()):
+        with pytest.raises(ValueError):
+            k(X, X2, full_cov=False)
+
+
+def test_diag_equals_diagonal_of_full():
+    """test_kernels.py:322-327 (test_diags)."""
+    X = np.random.RandomState(1).randn(15, 3)
+    for k in (O.SquaredExponential(0.7, 1.3), O.Matern12(), O.Linear(0.4), O.Polynomial(2.0, 0.5, 0.9), O.Constant(0.3), O.White(0.2),
+              O.Matern52() * O.Linear() + O.White(0.1)):
+        np.testing.assert_allclose(k(X, full_cov=False), np.diag(k(X)), rtol=1e-6)  # Matern12: sqrt(eps) noise on the diagonal (ops.py:109-111)
+
+
+# ---- tests/gpflow/test_kullback_leiblers.py, conditionals/test_conditionals.py -------------------------------------
+@pytest.mark.parametrize("shared_k", [True, False])
+@pytest.mark.parametrize("diag", [True, False])
+def test_sumkl_equals_batchkl(shared_k, diag):
+    """test_kullback_leiblers.py:166-192: gauss_kl sums the per-column KLs (kullback_leiblers.py:72-74)."""
+    rng = np.random.RandomState(0)
+    M, N = 5, 4
+    mu = rng.randn(M, N)
+    sqrt = np.stack([np.tril(rng.randn(M, M)) for _ in range(N)])
+    sqrt_diag = rng.rand(M, N) + 0.1
+    A = rng.randn(M, M)
+    K = A @ A.T + 1e-3 * np.eye(M)
+    K_batch = np.stack([K * (1.0 + 0.1 * n) for n in range(N)])
+    s = sqrt_diag if diag else sqrt
+    kl_batch = O.gauss_kl(mu, s, K if shared_k else K_batch)
+    kl_sum = 0.0
+    for n in range(N):
+        s_n = sqrt_diag[:, n][:, None] if diag else sqrt[n][None]
+        K_n = K if shared_k else K_batch[n][None]
+        kl_sum += O.gauss_kl(mu[:, n][:, None], s_n, K=K_n)
+    assert abs(kl_sum - kl_batch) < 1e-9 * max(1.0, abs(kl_batch))
+
+
+@pytest.mark.parametrize("white", [True, False])
+def test_conditional_diag_q_sqrt_equals_cholesky_q_sqrt(white):
+    """conditionals/test_conditionals.py:68-84 (test_diag) on the fixture of :28-66 (RandomState(123), Nn=10, Mn=20,
+    Ln=2, Matern32 + White(0.01))."""
+    rng = np.random.RandomState(123)
+    Nn, Mn, Ln = 10, 20, 2
+    Xs, X = rng.rand(Nn, 1), rng.rand(Mn, 1)
+    k = O.Matern32() + O.White(0.01)
+    mu = rng.rand(Mn, Ln)
+    sqrt = rng.rand(Mn, Ln)
+    chol = np.stack([np.diag(sqrt[:, i]) for i in range(Ln)])
+    Kmm = k(X) + 1e-6 * np.eye(Mn)
+    Kmn, Knn = k(X, Xs), k(Xs, full_cov=False)
+    m1, v1 = O.base_conditional(Kmn, Kmm, Knn, mu, q_sqrt=sqrt, white=white)
+    m2, v2 = O.base_conditional(Kmn, Kmm, Knn, mu, q_sqrt=chol, white=white)
+    np.testing.assert_allclose(m1, m2, atol=1e-12)
+    np.testing.assert_allclose(v1, v2, atol=1e-12)
