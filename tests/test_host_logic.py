@@ -209,3 +209,22 @@ def test_kernel_expressions_pass_the_host_compile_path_without_gpu():
     bad[0][0].op = 99
     assert lib.gpk_kbuild(bad[0], bad[1], bad[2], bad[3], ptr, 4, 4, None, 4, 0, 4, ptr, 4, _lib.GPK_F64, 0, 0.0, None, None) == -1
     assert b"unknown kernel op" in lib.gpk_last_error()
+
+
+def test_product_kernel_error_behaviour_matches_reference_without_gpu():
+    """Same exceptions as the reference, raised before any device work: full_cov=False with X2 (kernels/base.py:203-204,
+    tests/gpflow/kernels/test_kernels.py:621-627), ARD size mismatch (base.py:164-168, test_kernels.py:471-491), unknown
+    keyword (stationaries.py:56-58), on_separate_dimensions (base.py:256-278, test_kernels.py:607-618)."""
+    K = gpf.kernels
+    X, X2 = np.random.randn(4, 1), np.random.randn(5, 1)
+    for k in (K.RBF(), K.Matern32() + K.White(), K.Linear() * K.Constant(), K.Polynomial()):
+        with pytest.raises(ValueError):
+            k(X, X2, full_cov=False)
+    with pytest.raises(ValueError):
+        K.RBF(lengthscales=[1.0, 2.0, 3.0], active_dims=[0, 1])
+    with pytest.raises(TypeError):
+        K.RBF(foo=1)
+    k1, k2, k3 = K.Linear(active_dims=[1, 2, 3]), K.RBF(active_dims=[4, 5, 6]), K.RBF(active_dims=[3, 4, 5])
+    assert (k1 + k2).on_separate_dimensions is True
+    assert (k1 + k3).on_separate_dimensions is False
+    assert (K.Linear() + K.RBF()).on_separate_dimensions is False
