@@ -10,12 +10,14 @@
 //
 // A pre-pass (split_tiles_kernel) reads each operand once in whatever orientation it is stored,
 // splits hi/lo and writes PRE-TILED K-major planes in the canonical no-swizzle UMMA shared-memory
-// image, so the main kernel fills a pipeline stage with two 1-D bulk copies and never needs a
-// transposed (MN-major) descriptor.  Persistent CTAs, 192 threads:
-//   warp 0 producer (cp.async.bulk + mbarrier), warp 1 MMA issuer (one elected lane, 3 MMAs per
-//   8-deep k-step, tile 128 x 256, TWO 256-column TMEM accumulators so the epilogue of tile i overlaps
-//   the MMAs of tile i+1), warps 2-5 epilogue (tcgen05.ld -> shared transpose -> coalesced 128-byte
-//   row segments, alpha/beta, optional split-K atomics, optional fused column sums of squares).
+// image, so the main kernel fills a pipeline stage with 1-D bulk copies and never needs a
+// transposed (MN-major) descriptor.  Persistent CTAs, 320 threads:
+//   warp 0 producer (cp.async.bulk + mbarrier; in a 2-CTA cluster each CTA fetches half of every B plane
+//   and multicasts it), warp 1 MMA issuer (one elected lane, 3 MMAs per 8-deep k-step, tile 128 x 256,
+//   runs of 64 k-elements into alternating TMEM buffers), warps 2-9 promotion + epilogue (tcgen05.ld of a
+//   finished run, round-to-nearest add into fp32 register accumulators, then shared transpose -> coalesced
+//   128-byte row segments, alpha/beta, optional split-K atomics, optional fused column sums of squares).
+// The all-zero K range of a triangular A operand is skipped (tf_krange).
 #include <algorithm>
 #include <map>
 #include <utility>
