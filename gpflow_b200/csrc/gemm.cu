@@ -1,14 +1,14 @@
 // gemm.cu — general row-major GEMM  C = alpha*op(A)*op(B) + beta*C  for the Cholesky trailing
 // update (SYRK), the inverse-based TRSM steps, A A^T, A^T f and tril(q_sqrt)^T A.
 //   fp64: legacy tensor path  mma.sync.m8n8k4.f64 (DMMA) — tcgen05 has no f64 kind;
-//         the tcgen05 paths (int8-sliced fp64, 3xTF32 fp32) live in gemm_tc.cu.
-//   fp32: CUDA-core 128x128x8 register-tiled kernel (generic fallback for ragged shapes).
+//         the tcgen05 paths live in gemm_tc.cu (int8-sliced fp64 SYRK) and gemm_tf32.cu (3xTF32 fp32 GEMM).
+//   fp32: CUDA-core register-tiled kernel with the same tile-shape menu as the DMMA kernel (small / ragged shapes).
 // Replaces tf.linalg.matmul call sites: gpflow/models/sgpr.py:205,263, conditionals/util.py:144,157,
 // posteriors.py:497,535,539,728,734, and the GEMM inside tf.linalg.cholesky / triangular_solve.
 //
 // In-place contract used by potrf/trsm: a CTA reads every A/B element it needs before its first
-// store to C, and C tiles are 128x128, so C may alias A when n <= 128 (one column tile) and may
-// alias B when m <= 128 (one row tile).
+// store to C, so C may alias A when one tile spans n and may alias B when one tile spans m (the shape
+// selection keeps BN >= n resp. BM >= m in those cases).
 #include "common.cuh"
 
 namespace gpk {

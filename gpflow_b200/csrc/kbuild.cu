@@ -9,6 +9,9 @@
 // (utilities/model_utils.py:33-38, covariances/kuus.py:33) and writes K once with 16-byte
 // vector stores.  The reference materialises one [N,N2] temporary per elementwise op instead.
 //
+// A single stationary leaf takes the fast path further down (persistent CTAs, register-prefetched operand
+// pipeline, folded scales, table-driven exp / MUFU-seeded sqrt, lower tiles only + mirrored stores).
+//
 // Algorithmic HBM bytes per launch: T*(N*N2 + (N+N2)*D)  (GPK_LOWER: T*(N(N+1)/2 + N*D)).
 #include <math.h>
 #include <stdarg.h>

@@ -7,9 +7,14 @@
 //
 // Structure (row-major, lower): recursive blocked factorisation whose leaves are 128x128 diagonal
 // blocks handled by ONE CTA entirely in shared memory (warp-cooperative 32x32 register Cholesky,
-// per-row panel solves, 4x4 register-tiled updates) which also emits the INVERSE of the diagonal
-// block; every off-diagonal operation — panel solve X = B L_jj^-T, trailing update C -= A A^T,
-// forward/back substitution blocks — is then a dense GEMM (gemm.cu / gemm_tc.cu) with K >= 128.
+// per-row substitution panels, 4x4 register-tiled updates with in-leaf look-ahead).
+//   fp64, n > 128 ("slim"): the leaf also emits the inverses of its two 64x64 diagonal sub-blocks and
+//   potrf_panel_kernel solves the rows below on DMMA; the full 128x128 block inverses that trsm consumes
+//   are produced afterwards, all blocks in parallel (trtri_diag_kernel).
+//   fp32 / single block: the leaf emits the INVERSE of the whole diagonal block and the panel solve
+//   X = B L_jj^-T is one dense GEMM with it.
+// Trailing updates C -= A A^T (gemm.cu / gemm_tc.cu / gemm_tf32.cu, K >= 128) publish progress on the next
+// diagonal block so that the next leaf overlaps them on a side stream (look-ahead).
 // Rows below the square part (`rows > n`) ride along, so appending (Y-m)^T as extra rows yields
 // alpha^T = (L^-1 (Y-m))^T without a separate TRSV (logdensities.py:150).
 #include <map>
