@@ -152,3 +152,35 @@ def test_tf32_krange_splits_partition_the_needed_range(tri):
                     nonzero = True if tri == 0 else (k_lo <= r_hi if tri == 1 else k_hi >= r_lo)
                     if nonzero:
                         assert kb in stages, (tri, k, nsplit, cl, tm, kb)
+
+
+# ---- look-ahead progress counters (common.cuh::diag_units_total / diag_units_tile) ---------------------------------
+def diag_units_total(m, n):
+    a, b = min(m, 128), min(n, 128)
+    return -(-a // 32) * -(-b // 32)
+
+
+def diag_units_tile(m0, n0, bm, bn, m, n):
+    if m0 >= 128 or n0 >= 128:
+        return 0
+    a, b = min(m, 128) - m0, min(n, 128) - n0
+    ra, rb = min(a, bm), min(b, bn)
+    if ra <= 0 or rb <= 0:
+        return 0
+    return -(-ra // 32) * -(-rb // 32)
+
+
+@pytest.mark.parametrize("bm,bn", [(128, 128), (64, 128), (32, 128), (128, 64), (128, 32)])
+def test_head_tiles_publish_exactly_the_units_the_next_leaf_waits_for(bm, bn):
+    """Every GEMM tile shape (gemm.cu DMMA / SIMT shapes; 128x64 is also the tcgen05 int8 tile) must publish, over the
+    tiles it actually computes under GPK_GEMM_LOWER_ONLY, exactly diag_units_total(m, n) units: fewer and the waiting
+    leaf traps, more and it starts before its inputs are complete."""
+    for m, n in [(128, 128), (200, 128), (1000, 128), (4096, 4096), (129, 1), (640, 100), (96, 96), (7000, 4096), (130, 130)]:
+        published = 0
+        for m0 in range(0, m, bm):
+            for n0 in range(0, n, bn):
+                if n0 > m0 + bm - 1:        # lower-only: tile strictly above the diagonal is skipped
+                    continue
+                if n0 < 128:                # kernels publish only for tiles in the first 128 columns
+                    published += diag_units_tile(m0, n0, bm, bn, m, n)
+        assert published == diag_units_total(m, n), (bm, bn, m, n)
