@@ -184,3 +184,49 @@ def test_head_tiles_publish_exactly_the_units_the_next_leaf_waits_for(bm, bn):
                 if n0 < 128:                # kernels publish only for tiles in the first 128 columns
                     published += diag_units_tile(m0, n0, bm, bn, m, n)
         assert published == diag_units_total(m, n), (bm, bn, m, n)
+
+
+# ---- pre-tiled operand layouts (canonical no-swizzle K-major UMMA images) ----------------------------------------------
+def test_pretiled_plane_offsets_are_bijective_and_core_matrix_shaped():
+    """tc_tile_off (gemm_tc.cu: int8, 128 rows x 32 B) and tf_tile_off (gemm_tf32.cu: tf32, RB rows x 16 k x 4 B):
+    every (row, k) maps to a distinct offset inside the plane, the 8-row x 16-byte core matrices are contiguous
+    128-byte blocks, and a 256-row B plane is the concatenation of two 128-row planes (what lets 2-CTA clusters and
+    the A/B tile sizes share one layout)."""
+    def tc_off(r, k):
+        return (r >> 3) * 256 + (k >> 4) * 128 + (r & 7) * 16 + (k & 15)
+
+    offs = {tc_off(r, k) for r in range(128) for k in range(32)}
+    assert offs == set(range(128 * 32))
+    for rg in range(16):
+        for kc in range(2):
+            blk = {tc_off(rg * 8 + r, kc * 16 + b) for r in range(8) for b in range(16)}
+            assert blk == set(range(min(blk), min(blk) + 128))
+
+    def tf_off(r, k):
+        return (r >> 3) * 512 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4
+
+    for RB in (128, 256):
+        offs = {tf_off(r, k) + b for r in range(RB) for k in range(16) for b in range(4)}
+        assert offs == set(range(RB * 64))
+    assert all(tf_off(128 + r, k) == 128 * 64 + tf_off(r, k) for r in range(128) for k in range(16))
+
+
+def test_kbuild_lower_tile_decode_fp32_estimate():
+    """kbuild_fast_kernel decodes t = by (by + 1) / 2 + bx from an fp32 square-root estimate plus fix-up loops; the
+    estimate must stay within a step or two of the truth up to the 2^31 tile limit the host enforces."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    ts = np.concatenate([np.arange(0, 5000), rng.integers(0, 2 ** 31 - 1, 20000), [2 ** 31 - 2]])
+    for t in ts:
+        t = int(t)
+        by = int((np.sqrt(np.float32(8.0) * np.float32(t) + np.float32(1.0), dtype=np.float32) - np.float32(1.0)) * np.float32(0.5))
+        steps = 0
+        while by * (by + 1) // 2 > t:
+            by -= 1
+            steps += 1
+        while (by + 1) * (by + 2) // 2 <= t:
+            by += 1
+            steps += 1
+        bx = t - by * (by + 1) // 2
+        assert 0 <= bx <= by and steps <= 3, (t, by, bx, steps)
