@@ -45,3 +45,29 @@ def gpr_lml_threaded(X, Y, kernel, noise_variance, threads: int | None = None) -
     L = O.cholesky(K)                                  # gpr.py:102
     m = np.zeros_like(Y)
     return float(np.sum(O.multivariate_normal(Y, m, L)))  # logdensities.py:139-156, gpr.py:107
+
+
+class ThreadedKernel:
+    """Proxy around an oracle kernel: rectangular evaluations kernel(Z, X) with many columns (Kuf of the sparse models)
+    run in column blocks on a thread pool -- the same arithmetic, block by block, so the values are bit-identical.
+    Used only by the timed CPU arm so that its covariance builds use all host cores like its BLAS calls do."""
+
+    def __init__(self, kernel, threads: int | None = None, block: int = 2048):
+        self._k, self._threads, self._block = kernel, threads or os.cpu_count() or 1, block
+
+    def __getattr__(self, name):
+        return getattr(self._k, name)
+
+    def __call__(self, X, X2=None, *, full_cov=True, presliced=False):
+        if X2 is None or not full_cov or presliced or X2.shape[0] < 4 * self._block:
+            return self._k(X, X2, full_cov=full_cov, presliced=presliced)
+        N2 = X2.shape[0]
+        out = np.empty((X.shape[0], N2), dtype=X.dtype)
+
+        def work(j0: int) -> None:
+            j1 = min(N2, j0 + self._block)
+            out[:, j0:j1] = self._k(X, X2[j0:j1])
+
+        with ThreadPoolExecutor(max_workers=self._threads) as ex:
+            list(ex.map(work, range(0, N2, self._block)))
+        return out
