@@ -10,7 +10,9 @@ synthetic data of SURVEY.md 8(d).  One "step" = one full evaluation.
                                                            algorithm on all host cores (TensorFlow is not
                                                            installable here)
 Under torchrun (N>1) every rank evaluates its own replica / shard (weak scaling) and the scalar
-objectives are summed with ONE NCCL all-reduce per step; timing = CUDA events, max over ranks.
+objectives are summed with ONE asynchronous NCCL all-reduce per step (off the critical path, all complete inside the
+timed region); timing = CUDA events, max over ranks.  Every line also carries BASELINE configs[3] (SVGP, 8 latent GPs)
+on the same GPUs in each sharding mode of SURVEY 8(e) (`svgp_c4`).
 Prints exactly one JSON line on rank 0.
 """
 from __future__ import annotations
@@ -335,7 +337,7 @@ def run_reference(args):
         "impl": "reference", "metric": "objective_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if hp["dtype"] == np.float64 else "f32",
-        "data": "synthetic", "config": {"workload": WORKLOADS[name][1], "objective": float(val)},
+        "data": "synthetic", "config": {"workload": WORKLOADS[name][1]}, "objective": float(val),
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full evaluations of the workload (NumPy/SciPy+OpenBLAS oracle port of "
                                    "the reference algorithm; TensorFlow not installable, see DESIGN.md)"},
@@ -346,7 +348,133 @@ def run_reference(args):
     return 0
 
 
+def pin_to_gpu_numa_node(local: int):
+    """Pins this rank's host threads to the CPUs NVML reports as local to its GPU (ranks of GPUs 4-7 sit on the
+    second NUMA node of these boxes).  Returns the previous affinity so that the CPU-baseline leg can have all cores."""
+    prev = None
+    try:
+        import pynvml
+        import torch
+
+        prev = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+    except Exception:  # noqa: BLE001  (best effort: an unpinned rank is still correct)
+        pass
+    return prev
+
+
+def step_stats(per_rank_ms):
+    """per_rank_ms [world, steps] -> summary that tells a one-off stall from a per-step cost."""
+    a = np.asarray(per_rank_ms, dtype=np.float64)
+    worst = a.max(axis=0)  # slowest rank of every step
+    return {"median_ms": float(np.median(worst)), "min_ms": float(worst.min()), "max_ms": float(worst.max()),
+            "p95_ms": float(np.percentile(worst, 95)), "per_rank_median_ms": [float(x) for x in np.median(a, axis=1)],
+            "steps_over_1p5x_median": int((worst > 1.5 * np.median(worst)).sum())}
+
+
+def timed_loop(torch, dist, steps, one_step, slots):
+    """`steps` iterations of one_step(i) -> device fp64 scalar.  The scalar of step i goes to slots[i] and is summed over
+    the ranks by an ASYNCHRONOUS all-reduce (its own NCCL stream): step i+1 does not consume it, so the collective is
+    off the critical path; all of them are complete before the closing event.  Device-timed, barrier + synchronize on
+    both sides.  Returns (total ms on this rank, per-step ms list)."""
+    works = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(steps):
+        v = one_step(i)
+        slot = slots[i:i + 1]
+        slot.copy_(v.reshape(1))
+        if dist is not None:
+            works.append(dist.all_reduce(slot, async_op=True))  # ONE scalar all-reduce per evaluation (SURVEY 8(e))
+        ev[i + 1].record()
+    for w in works:
+        w.wait()
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(end), per_step
+
+
+def gather_ms(torch, dist, world, ms_total, per_step):
+    """max over ranks of the region time + the [world, steps] table of per-step times."""
+    if dist is None:
+        return ms_total, [per_step]
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mine = torch.tensor(per_step, dtype=torch.float64, device="cuda")
+    allv = torch.empty((world, len(per_step)), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(allv.view(-1), mine)
+    return float(t.item()), allv.cpu().numpy().tolist()
+
+
+def svgp_c4_modes(args, torch, dist, rank, world):
+    """BASELINE configs[3] on the N GPUs of this run, in the sharding modes of SURVEY 8(e) (gpflow_b200/sharding.py):
+    independent minibatches (throughput), rows of ONE minibatch, latent GPs of ONE minibatch with the column-sharded
+    solve + all-gather.  Every mode: device-timed, max over ranks, the async scalar all-reduce inside the region."""
+    import gpflow_b200 as gpf
+    from gpflow_b200 import sharding
+
+    prev_float, prev_jit = gpf.config.default_float(), gpf.config.default_jitter()
+    hp = host_problem("svgp_c4", rank)
+    arm = OurArm("svgp_c4", hp, rank, world)
+    arm.build_resident()
+    model = arm.models[0]
+    steps = args.steps
+    slots = torch.zeros(steps, dtype=torch.float64, device="cuda")
+    # one SHARED minibatch sequence for the single-minibatch modes (every rank holds the same rows)
+    shared = []
+    for i in range(4):
+        idx = hp["perm"][i * hp["B"]:(i + 1) * hp["B"]]
+        shared.append((gpf.ops.to_device(hp["X"][idx]), gpf.ops.to_device(hp["Y"][idx])))
+    modes = {
+        "independent_minibatches": lambda i: arm.eval_resident(),
+        "rows_of_one_minibatch": lambda i: sharding.svgp_elbo_row_sharded(model, shared[i % 4], rank, world)[0],
+        "latents_of_one_minibatch": lambda i: sharding.svgp_elbo_latent_sharded(model, shared[i % 4], rank, world)[0],
+        "latents_no_sharded_solve": lambda i: sharding.svgp_elbo_latent_sharded(model, shared[i % 4], rank, world,
+                                                                                shard_solve=False)[0],
+    }
+    out = {}
+    full = None
+    for name, fn in modes.items():
+        internal_reduce = name != "independent_minibatches"  # the sharded modes all-reduce inside (the share IS the step)
+        for i in range(3):
+            fn(i)
+        ms, per = timed_loop(torch, None if internal_reduce else dist, steps, fn, slots)
+        if internal_reduce and dist is not None:
+            dist.barrier()
+        ms, table = gather_ms(torch, dist, world, ms, per)
+        evals = (world if name == "independent_minibatches" else 1) * steps / (ms * 1e-3)
+        out[name] = {"evals_per_s": evals, "ms_per_step": ms / steps, "step_stats": step_stats(table)}
+        if name != "independent_minibatches":
+            val = float(fn(0).item())
+            if full is None:
+                full = float(model.elbo(shared[0]).item())
+            out[name]["sum_of_shares_vs_full_rel_err"] = abs(val - full) / max(abs(full), 1e-300)
+    out["config"] = WORKLOADS["svgp_c4"][1]
+    out["n_gpus"] = world
+    out["note"] = ("independent_minibatches = the throughput mode the north star's >= 6x refers to (weak scaling, one "
+                   "minibatch per GPU per step); the one-minibatch modes are strong scaling and pay the replicated "
+                   "chol(Kuu) of M = 2048 on every rank")
+    gpf.config.set_default_float(prev_float)
+    gpf.config.set_default_jitter(prev_jit)
+    del arm, model, shared
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
+    import ctypes
+
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -355,6 +483,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    prev_affinity = pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -370,53 +499,46 @@ def run_ours(args):
     hp = host_problem(name, rank)
     arm = OurArm(name, hp, rank, world)
     arm.build_resident()
-    red = torch.zeros(1, dtype=torch.float64, device="cuda")
+    steps = args.steps
+    warm = max(args.warmup, 3)
+    slots = torch.zeros(steps, dtype=torch.float64, device="cuda")
 
-    def step_resident():
-        v = arm.eval_resident()
-        red.copy_(v.reshape(1))
-        if dist is not None:
-            dist.all_reduce(red)  # ONE scalar all-reduce per evaluation
-        return red
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
+    for i in range(warm):
+        arm.eval_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     lib.gpk_launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    barrier()
+    ms_total, per_step = timed_loop(torch, dist, steps, lambda i: arm.eval_resident(), slots)
     launches = int(lib.gpk_launch_count())
-    ms_total = e0.elapsed_time(e1)
-    objective = float(red.item()) / world
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    objective = float(slots[-1].item()) / world
+    ms_total, table = gather_ms(torch, dist, world, ms_total, per_step)
+    ms_step = ms_total / steps
     value = world / (ms_step * 1e-3)
 
-    # instrumented pass: the same K steps with CUDA events around every launch (per-kernel-class time)
-    import ctypes
+    # value + gradient evaluations (training step of the Scipy optimiser contract), when the model has a device backward
+    grad = None
+    if name in ("gpr_c2", "gpr_c1") and hasattr(arm.models[0], "log_marginal_likelihood_and_grad"):
+        m0 = arm.models[0]
+        for _ in range(2):
+            m0.log_marginal_likelihood_and_grad()
+        gsteps = max(3, steps // 4)
+        gms, _ = timed_loop(torch, None, gsteps, lambda i: m0.log_marginal_likelihood_and_grad()[0], slots)
+        gms, _ = gather_ms(torch, dist, world, gms, [0.0])
+        grad = {"value_and_grad_evals_per_s": world * gsteps / (gms * 1e-3), "ms_per_step": gms / gsteps, "steps": gsteps}
+
+    # instrumented pass: the same K steps with CUDA events around every launch (per-kernel-class time and issued work)
+    NC = 8
     lib.gpk_prof_enable(1)
-    for _ in range(args.steps):
-        step_resident()
-    msv = (ctypes.c_double * 5)()
-    cnt = (ctypes.c_int64 * 5)()
-    lib.gpk_prof_read(msv, cnt, 5)
+    for _ in range(steps):
+        arm.eval_resident()
+    msv, cnt, wk = (ctypes.c_double * NC)(), (ctypes.c_int64 * NC)(), (ctypes.c_double * NC)()
+    lib.gpk_prof_read2(msv, cnt, wk, NC)
     lib.gpk_prof_enable(0)
-    prof = {k: {"ms_per_step": msv[i] / args.steps, "launches_per_step": cnt[i] / args.steps}
-            for i, k in enumerate(["kbuild", "gemm", "potrf_leaf", "gemm_skinny", "misc"])}
+    cls_names = ["kbuild", "gemm_dmma_simt", "potrf_leaf", "gemm_skinny", "misc", "tcgen05", "panel_solve"]
+    prof = {k: {"ms_per_step": msv[i] / steps, "launches_per_step": cnt[i] / steps, "issued_macs_per_step": wk[i] / steps}
+            for i, k in enumerate(cls_names)}
     clocks = sampler.stop() if sampler is not None else None
+    pk_probe = (ctypes.c_double * 4)()
+    lib.gpk_peak_probe(pk_probe, None)
 
     # standalone K-build of the FULL symmetric matrix (the reference's `kernel(X)` op): CUDA events around
     # K launches of gpk_kbuild alone, output = 8*N^2 bytes > L2
@@ -432,30 +554,41 @@ def run_ours(args):
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             _ops.kbuild(desc, Xd, None, out=Kbuf)
         k1.record()
         torch.cuda.synchronize()
-        kfull = k0.elapsed_time(k1) / args.steps
+        kfull = k0.elapsed_time(k1) / steps
         del Kbuf
 
     # end-to-end through the public API from pinned HOST buffers (H2D + evaluation + D2H every step)
     pinned = arm.pinned_inputs()
     for _ in range(3):
         arm.eval_e2e(pinned)
-    barrier()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         val, h2d, d2h = arm.eval_e2e(pinned)
     e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / steps
     if dist is not None:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world / (e2e_ms * 1e-3)
+
+    # BASELINE configs[3] (SVGP, 8 latent GPs) on the same GPUs, every sharding mode: the multi-GPU row of the north star
+    svgp = None
+    if not args.no_svgp and name != "svgp_c4":
+        del pinned
+        svgp = svgp_c4_modes(args, torch, dist, rank, world)
 
     if rank != 0:
         if dist is not None:
@@ -464,30 +597,64 @@ def run_ours(args):
 
     pk = peaks()
     work = algorithmic_work(name, hp)
-    gemm_s = prof["gemm"]["ms_per_step"] * 1e-3
+    f64 = hp["dtype"] == np.float64
+    tc_s, dm_s, pn_s = (prof[k]["ms_per_step"] * 1e-3 for k in ("tcgen05", "gemm_dmma_simt", "panel_solve"))
     kb_s = prof["kbuild"]["ms_per_step"] * 1e-3
-    ach = work["chol_flops"] / gemm_s / 1e12 if gemm_s > 0 else 0.0
-    peak = pk["bf16_sustained"]
-    roofline = {
-        "bound": "tensor", "kernel": "Cholesky GEMM class: syrk_i8_kernel (tcgen05 kind::i8, digit-sliced fp64 SYRK, K >= 512 "
-        "levels) + gemm_dmma_kernel + potrf_panel_kernel" if hp["dtype"] == np.float64
-        else "GEMM class: gemm_tf32_kernel (tcgen05 kind::tf32 x3) + gemm_simt_kernel",
-        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
-        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "pipe": "tcgen05 int8 (28 digit MMAs per 32-deep fp64 k-step; tcgen05 has no f64 kind) above K = 512, fp64 DMMA "
-        "mma.sync.m8n8k4 below; achieved = ALGORITHMIC fp64 flops / class time" if hp["dtype"] == np.float64
-        else "tcgen05 kind::tf32 (3 MMAs per fp32 product) + fp32 FFMA for small shapes",
-        "ncu_tensor_pipe_active": {"syrk_i8_kernel": 0.518, "gemm_tf32_kernel": 0.535,
-                                   "source": "profiles/ncu/r1_syrk_v2_raw.csv, r1_tf32_v2_raw.csv (one launch each)"},
-        "pipe_peak_tflops_nominal": 37.0 if hp["dtype"] == np.float64 else 74.0,
-        "pipe_frac_nominal": ach / (37.0 if hp["dtype"] == np.float64 else 74.0),
-        "algorithmic_flops_per_step": work["chol_flops"], "launches_per_step": prof["gemm"]["launches_per_step"],
-        "kernel_ms_per_step": prof["gemm"]["ms_per_step"],
-        "share_of_step": prof["gemm"]["ms_per_step"] / ms_step,
-    }
+    tc_macs = prof["tcgen05"]["issued_macs_per_step"]
+    i8_peak, dmma_peak = float(pk_probe[0]), float(pk_probe[1])
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    if f64:
+        ach = 2.0 * tc_macs / tc_s / 1e12 if tc_s > 0 else 0.0
+        S = int(lib.gpk_potrf_last_slices()) or 7
+        roofline = {
+            "bound": "tensor",
+            "kernel": "syrk_i8_kernel (tcgen05 kind::i8: fp64 operands as S signed 7-bit digit planes, S(S+1)/2 digit "
+                      "MMAs per 32-deep k-step, exact int32 accumulation in TMEM; tcgen05 has no f64 kind)",
+            "achieved": ach, "peak": i8_peak, "unit": "TFLOP/s", "frac": ach / i8_peak if i8_peak else None,
+            "ops": "int8 operations ISSUED by the launches of this kernel (2 per MAC, padding tiles included) / summed "
+                   "duration of those launches (CUDA events on the launch stream)",
+            "peak_source": "tcgen05 kind::i8 issue peak measured in this run on this GPU (gpk_peak_probe: 128x256x32 MMAs, "
+                           "operands resident in shared memory, all SMs); MEASURED_PEAKS.json holds bf16 only",
+            "peak_bf16_measured_for_context": {"tflops_sustained": pk["bf16_sustained"], "source": pk["source"],
+                                               "frac_vs_2x_bf16": ach / (2.0 * pk["bf16_sustained"])},
+            "slices": S, "digit_mmas_per_fp64_kstep": S * (S + 1) // 2,
+            "fp64_equivalent_tflops": (2.0 * tc_macs / (S * (S + 1) / 2)) / tc_s / 1e12 if tc_s > 0 else 0.0,
+            "kernel_ms_per_step": prof["tcgen05"]["ms_per_step"], "launches_per_step": prof["tcgen05"]["launches_per_step"],
+            "share_of_step": prof["tcgen05"]["ms_per_step"] / ms_step,
+            "traffic": ncu.get("syrk_i8_dram_bytes_per_launch"),
+            "traffic_source": ncu.get("syrk_i8_source"),
+            "dmma_class": {"kernels": "gemm_dmma_kernel (K < 512 trailing updates) + potrf_panel_kernel, mma.sync.m8n8k4.f64",
+                           "achieved_tflops": 2.0 * prof["gemm_dmma_simt"]["issued_macs_per_step"] / dm_s / 1e12 if dm_s > 0 else 0.0,
+                           "peak_tflops": dmma_peak, "peak_source": "gpk_peak_probe (DMMA, registers only, all SMs)",
+                           "ms_per_step": prof["gemm_dmma_simt"]["ms_per_step"], "panel_ms_per_step": prof["panel_solve"]["ms_per_step"]},
+            "whole_factorisation": {"algorithmic_fp64_flops": work["chol_flops"],
+                                    "fp64_equivalent_tflops_of_the_step": work["chol_flops"] / (ms_step * 1e-3) / 1e12,
+                                    "frac_of_dmma_peak": work["chol_flops"] / (ms_step * 1e-3) / 1e12 / dmma_peak if dmma_peak else None},
+        }
+        if roofline["dmma_class"]["peak_tflops"]:
+            roofline["dmma_class"]["frac"] = roofline["dmma_class"]["achieved_tflops"] / dmma_peak
+    else:
+        ach = 2.0 * tc_macs / tc_s / 1e12 if tc_s > 0 else 0.0
+        tf32_peak = pk["bf16_sustained"] / 2.0
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, 3 MMAs per fp32 product: hi*hi + hi*lo + lo*hi)",
+            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            "ops": "tf32 operations ISSUED (2 per MAC, 3 MACs per fp32 product) / summed duration of the launches",
+            "peak_source": pk["source"] + ": half of the measured sustained bf16 rate (tf32 dense = bf16 / 2 on this part)",
+            "fp32_equivalent_tflops": ach / 3.0, "kernel_ms_per_step": prof["tcgen05"]["ms_per_step"],
+            "launches_per_step": prof["tcgen05"]["launches_per_step"], "share_of_step": prof["tcgen05"]["ms_per_step"] / ms_step,
+            "traffic": ncu.get("gemm_tf32_dram_bytes_per_launch"), "traffic_source": ncu.get("gemm_tf32_source"),
+        }
+    if svgp is not None:
+        roofline["svgp_c4"] = svgp
     kb_ach = work["kbuild_bytes_lower"] / kb_s / 1e9 if kb_s > 0 else 0.0
     kbuild = {"bound": "hbm", "achieved": kb_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kb_ach / pk["hbm_gbs"],
-              "algorithmic_bytes_per_step": work["kbuild_bytes_lower"], "ms_per_step": prof["kbuild"]["ms_per_step"],
+              "peak_source": pk["source"], "algorithmic_bytes_per_step": work["kbuild_bytes_lower"],
+              "ms_per_step": prof["kbuild"]["ms_per_step"], "traffic": ncu.get("kbuild_dram_bytes_per_launch"),
               "note": "inside the LML: lower-triangle tiles only (GPK_LOWER); fp64 exp/sqrt make it fp64-pipe / issue bound"}
     if kfull:
         fa = work["kbuild_bytes_full"] / (kfull * 1e-3) / 1e9
@@ -495,7 +662,12 @@ def run_ours(args):
                                  "algorithmic_bytes": work["kbuild_bytes_full"],
                                  "note": "standalone kernel(X): lower tiles computed once, mirrored tile stored straight from registers"}
 
-    # CPU baseline on this box's host cores: bounded sample = full evaluations for ~10-30 s
+    # CPU baseline on this box's host cores (all of them again): bounded sample = full evaluations for ~10-30 s
+    if prev_affinity is not None:
+        try:
+            os.sched_setaffinity(0, prev_affinity)
+        except Exception:  # noqa: BLE001
+            pass
     threads = os.cpu_count() or 1
     t0 = time.perf_counter()
     n_cpu = 0
@@ -515,19 +687,25 @@ def run_ours(args):
     rel = abs(check - cpu_val) / max(abs(cpu_val), 1e-300)
 
     line = {
-        "metric": "objective_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64" if hp["dtype"] == np.float64 else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[name][1], "parallelism": f"replicas x{world} + 1 scalar all-reduce" if world > 1 else "single GPU",
-                   "l2": "working set (K / Kuf matrix) exceeds the 126 MB L2, no flush between steps" if name not in ("gpr_c1",) else "fits L2 (plumbing config)",
-                   "objective": objective, "objective_vs_cpu_rel_err": rel},
+        "metric": "objective_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if f64 else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[name][1]},
+        "parallelism": f"replicas x{world}, 1 asynchronous scalar all-reduce per evaluation" if world > 1 else "single GPU",
+        "l2": "working set (K / Kuf matrix) exceeds the 126 MB L2, no flush between steps" if name not in ("gpr_c1",) else "fits L2 (plumbing config)",
+        "objective": objective, "objective_vs_cpu_rel_err": rel, "step_stats": step_stats(table),
         "roofline": roofline, "kbuild_roofline": kbuild, "kernel_classes": prof,
+        "pipe_peaks_probe": {"tcgen05_i8_tops": i8_peak, "dmma_fp64_tflops": dmma_peak, "sms": int(pk_probe[2])},
         "cpu_baseline": {"value": 1.0 / cpu_dt, "unit": "evals/s", "cores": threads, "kind": "port",
                          "sample": f"{n_cpu} full evaluation(s) of the same workload, NumPy/SciPy+OpenBLAS oracle port"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if grad is not None:
+        line["value_and_grad"] = grad
+    if svgp is not None:
+        line["svgp_c4"] = svgp
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -557,6 +735,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gpr_c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-svgp", action="store_true", help="skip the SVGP C4 sharding-mode section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

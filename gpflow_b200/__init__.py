@@ -6,10 +6,10 @@ from . import config
 from .config import default_float, default_jitter
 from .base import Module, Parameter
 from . import (conditionals, covariances, inducing_variables, kernels, kullback_leiblers, likelihoods,
-               logdensities, mean_functions, models, ops, posteriors, utilities)
+               logdensities, mean_functions, models, ops, optimizers, posteriors, sharding, utilities)
 from .utilities import set_trainable
 
 __version__ = "0.1.0"
 __all__ = ["Module", "Parameter", "conditionals", "config", "covariances", "default_float", "default_jitter",
            "inducing_variables", "kernels", "kullback_leiblers", "likelihoods", "logdensities", "mean_functions",
-           "models", "ops", "posteriors", "set_trainable", "utilities"]
+           "models", "ops", "optimizers", "posteriors", "set_trainable", "sharding", "utilities"]

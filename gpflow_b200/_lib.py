@@ -73,9 +73,15 @@ SIGNATURES = {
     "gpk_debug_leaf": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "gpk_prof_enable": (c_int, [c_int]),
     "gpk_prof_read": (c_int, [_F64, POINTER(c_int64), c_int]),
+    "gpk_prof_read2": (c_int, [_F64, POINTER(c_int64), _F64, c_int]),
+    "gpk_peak_probe": (c_int, [_F64, c_void_p]),
+    "gpk_potrf_last_slices": (c_int, []),
     "gpk_gpr_lml_ws": (c_size_t, [c_int64, c_int64, c_int]),
     "gpk_gpr_lml": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_double,
                             c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_gpr_lml_grad_ws": (c_size_t, [c_int64, c_int64, c_int]),
+    "gpk_gpr_lml_grad": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_double,
+                                 c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "gpk_sgpr_elbo_ws": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "gpk_sgpr_elbo": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                               c_void_p, c_int64, c_int64, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p,
@@ -84,6 +90,11 @@ SIGNATURES = {
     "gpk_svgp_elbo": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                               c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
                               c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_svgp_elbo_A": (c_size_t, [c_int64, c_int64, c_int64, c_int, POINTER(c_int64)]),
+    "gpk_svgp_elbo_staged": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                     c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
+                                     c_double, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
 }
 
 # GPFLOW_B200_LIB selects another build of the same ABI (kernel experiments); default = the in-tree library
@@ -109,6 +120,20 @@ def load() -> ctypes.CDLL:
             raise GpkError(
                 f"libgpk.so is missing and could not be built ({e}); gpflow_b200 has no CPU fallback"
             ) from e
+    elif "GPFLOW_B200_LIB" not in os.environ:
+        # a library older than its sources is a silent trap while developing kernels: rebuild when asked to, else warn
+        try:
+            from . import build as _build
+
+            if _build.needs_build():
+                if os.environ.get("GPFLOW_B200_AUTOBUILD") == "1":
+                    _build.build()
+                else:
+                    import sys
+                    sys.stderr.write("gpflow_b200: libgpk.so is older than csrc/ or include/gpk.h "
+                                     "(python -m gpflow_b200.build, or GPFLOW_B200_AUTOBUILD=1)\n")
+        except Exception:  # noqa: BLE001  (no nvcc on a deployment box: the shipped library is what runs)
+            pass
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -22,6 +22,11 @@ class Transform:
     def inverse(self, y: np.ndarray) -> np.ndarray:
         return y
 
+    def forward_grad(self, x: np.ndarray) -> np.ndarray:
+        """d forward(x) / dx, elementwise (chain rule from constrained to unconstrained gradients,
+        what tf autodiff applies through the bijector; gpflow/base.py:118-280)."""
+        return np.ones_like(np.asarray(x, dtype=np.float64))
+
 
 class Softplus(Transform):
     def forward(self, x):
@@ -31,6 +36,10 @@ class Softplus(Transform):
         y = np.asarray(y, dtype=np.float64)
         return y + np.log(-np.expm1(-y))
 
+    def forward_grad(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return 1.0 / (1.0 + np.exp(-x))
+
 
 class Exp(Transform):
     def forward(self, x):
@@ -38,6 +47,9 @@ class Exp(Transform):
 
     def inverse(self, y):
         return np.log(y)
+
+    def forward_grad(self, x):
+        return np.exp(np.asarray(x, dtype=np.float64))
 
 
 class Shifted(Transform):
@@ -51,6 +63,9 @@ class Shifted(Transform):
 
     def inverse(self, y):
         return self.base.inverse(np.asarray(y) - self.lower)
+
+    def forward_grad(self, x):
+        return self.base.forward_grad(x)
 
 
 class FillTriangular(Transform):
@@ -110,6 +125,18 @@ class Parameter:
     def unconstrained_variable(self) -> np.ndarray:
         return self._value if self.transform is None else self.transform.inverse(self._value)
 
+    def assign_unconstrained(self, u: Any) -> None:
+        """Sets the parameter from its unconstrained value (what an optimiser updates; gpflow/base.py:196-211)."""
+        u = np.asarray(u, dtype=np.float64).reshape(self._value.shape)
+        self.assign(u if self.transform is None else self.transform.forward(u))
+
+    def unconstrained_gradient(self, g_constrained: Any) -> np.ndarray:
+        """Chain rule: gradient w.r.t. the unconstrained variable from the gradient w.r.t. the constrained value."""
+        g = np.asarray(g_constrained, dtype=np.float64).reshape(self._value.shape)
+        if self.transform is None:
+            return g
+        return g * self.transform.forward_grad(self.unconstrained_variable)
+
     def assign(self, value: Any) -> None:
         if hasattr(value, "detach"):
             value = value.detach().cpu().numpy()
@@ -159,6 +186,12 @@ class Module:
     @property
     def trainable_parameters(self) -> Tuple[Parameter, ...]:
         return tuple(p for p in self.parameters if p.trainable)
+
+    @property
+    def trainable_variables(self) -> Tuple[Parameter, ...]:
+        """The handles an optimiser updates (tf.Module.trainable_variables in the reference): the trainable Parameters;
+        their `unconstrained_variable` / `assign_unconstrained` are the unconstrained view."""
+        return self.trainable_parameters
 
 
 def _walk_value(v: Any, seen: set) -> Iterator[Parameter]:

@@ -20,14 +20,15 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfRec { cudaEvent_t a, b; int cls; };
+struct ProfRec { cudaEvent_t a, b; int cls; double work; };
 static std::vector<ProfRec> g_recs;
 static bool g_prof = false;
 
-ProfScope::ProfScope(int cls, cudaStream_t s) : idx(-1), st(s) {
+ProfScope::ProfScope(int cls, cudaStream_t s, double work) : idx(-1), st(s) {
   if (!g_prof) return;
   ProfRec r;
   r.cls = cls;
+  r.work = work;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, s);
   g_recs.push_back(r);
@@ -47,10 +48,11 @@ int gemm_any(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, cons
 }
 
 int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws, cudaStream_t st,
-              bool need_dinv) {
+              bool need_dinv, double cond_hint) {
   const size_t tcb = potrf_tc_ws_bytes(n, rows, dtype);
   void* tcws = tcb ? (char*)ws + align_up(dinv_bytes(n, dtype), 256) + 256 : nullptr;
-  if (dtype == GPK_F64) return potrf_t<double>((double*)A, n, rows, lda, info, (double*)ws, tcws, tcb, st, need_dinv);
+  if (dtype == GPK_F64)
+    return potrf_t<double>((double*)A, n, rows, lda, info, (double*)ws, tcws, tcb, st, need_dinv, cond_hint);
   return potrf_t<float>((float*)A, n, rows, lda, info, (float*)ws, nullptr, 0, st, need_dinv);
 }
 
@@ -67,9 +69,14 @@ int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype,
 }
 
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st);
+int peak_probe(double* out_host, cudaStream_t st);
+int potrf_last_slices();
 size_t gpr_lml_ws(int64_t N, int64_t P, int dtype);
 int gpr_lml(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t, const void*,
             int64_t, double, const void*, int, double*, void*, cudaStream_t);
+size_t gpr_lml_grad_ws(int64_t N, int64_t P, int dtype);
+int gpr_lml_grad(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t,
+                 const void*, int64_t, double, int, double*, int, void*, cudaStream_t);
 size_t sgpr_elbo_ws(int64_t N, int64_t M, int64_t P, int dtype);
 int sgpr_elbo(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t, const void*,
               int64_t, const void*, int64_t, int64_t, double, double, int, double*, void*, void*, void*, void*,
@@ -77,7 +84,8 @@ int sgpr_elbo(const gpk_knode*, int, const int32_t*, const double*, const void*,
 size_t svgp_elbo_ws(int64_t B, int64_t M, int64_t P, int dtype);
 int svgp_elbo(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t, const void*,
               int64_t, const void*, int64_t, int64_t, const void*, const void*, int, int, double, double, double, int,
-              int, int, double*, void*, cudaStream_t);
+              int, int, double*, void*, cudaStream_t, int stage = 0, int64_t c0 = 0, int64_t c1 = 0);
+size_t svgp_elbo_A(int64_t B, int64_t M, int64_t P, int dtype, int64_t* ld);
 
 }  // namespace gpk
 
@@ -103,13 +111,26 @@ int gpk_prof_enable(int on) {
   return 0;
 }
 
-int gpk_prof_read(double* ms, int64_t* launches, int n) {
+int gpk_peak_probe(double* out_host, void* stream) {
+  GPK_CHECK_ARG(out_host, "peak_probe: bad arguments");
+  return peak_probe(out_host, (cudaStream_t)stream);
+}
+
+int gpk_prof_read(double* ms, int64_t* launches, int n) { return gpk_prof_read2(ms, launches, nullptr, n); }
+
+int gpk_potrf_last_slices(void) { return potrf_last_slices(); }
+
+int gpk_prof_read2(double* ms, int64_t* launches, double* work, int n) {
   GPK_CHECK_ARG(ms && launches && n > 0, "prof_read: bad arguments");
-  for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; if (work) work[i] = 0.0; }
   GPK_CUDA_OK(cudaDeviceSynchronize());
   for (auto& r : g_recs) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < n) { ms[r.cls] += t; launches[r.cls] += 1; }
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < n) {
+      ms[r.cls] += t;
+      launches[r.cls] += 1;
+      if (work) work[r.cls] += r.work;
+    }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
@@ -270,6 +291,29 @@ int gpk_svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* dims, cons
   GPK_DTYPE_OK("svgp_elbo");
   return svgp_elbo(nodes, n_nodes, dims, ard, Xb, B, ldx, D, Yc, P, Z, M, ldz, q_mu, q_sqrt, q_diag, whiten,
                    noise_variance, num_data_scale, jitter, p_begin, p_end, dtype, out, ws, (cudaStream_t)stream);
+}
+
+size_t gpk_gpr_lml_grad_ws(int64_t N, int64_t P, int dtype) { return gpr_lml_grad_ws(N, P, dtype); }
+
+int gpk_gpr_lml_grad(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* X, int64_t N,
+                     int64_t ldx, int64_t D, const void* Yc, int64_t P, double noise_variance, int dtype, double* out,
+                     int n_out, void* ws, void* stream) {
+  GPK_DTYPE_OK("gpr_lml_grad");
+  return gpr_lml_grad(nodes, n_nodes, dims, ard, X, N, ldx, D, Yc, P, noise_variance, dtype, out, n_out, ws,
+                      (cudaStream_t)stream);
+}
+
+size_t gpk_svgp_elbo_A(int64_t B, int64_t M, int64_t P, int dtype, int64_t* ld) { return svgp_elbo_A(B, M, P, dtype, ld); }
+
+int gpk_svgp_elbo_staged(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* Xb,
+                         int64_t B, int64_t ldx, int64_t D, const void* Yc, int64_t P, const void* Z, int64_t M,
+                         int64_t ldz, const void* q_mu, const void* q_sqrt, int q_diag, int whiten,
+                         double noise_variance, double num_data_scale, double jitter, int p_begin, int p_end, int stage,
+                         int64_t col_begin, int64_t col_end, int dtype, double* out, void* ws, void* stream) {
+  GPK_DTYPE_OK("svgp_elbo_staged");
+  return svgp_elbo(nodes, n_nodes, dims, ard, Xb, B, ldx, D, Yc, P, Z, M, ldz, q_mu, q_sqrt, q_diag, whiten,
+                   noise_variance, num_data_scale, jitter, p_begin, p_end, dtype, out, ws, (cudaStream_t)stream, stage,
+                   col_begin, col_end);
 }
 
 }  // extern "C"

@@ -5,6 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/gpk.h"
 
 namespace gpk {
@@ -16,10 +19,11 @@ void count_launch();
 struct ProfScope {
   int idx;
   cudaStream_t st;
-  ProfScope(int cls, cudaStream_t s);
+  ProfScope(int cls, cudaStream_t s, double work = 0.0);  // work: operations ISSUED by the launch (class-specific unit)
   ~ProfScope();
 };
-enum { PROF_KBUILD = 0, PROF_GEMM = 1, PROF_LEAF = 2, PROF_SKINNY = 3, PROF_MISC = 4 };
+// PROF_GEMM: DMMA / SIMT GEMMs, PROF_TC: tcgen05 kernels (work = int8 or tf32 MACs issued), PROF_PANEL: potrf_panel_kernel
+enum { PROF_KBUILD = 0, PROF_GEMM = 1, PROF_LEAF = 2, PROF_SKINNY = 3, PROF_MISC = 4, PROF_TC = 5, PROF_PANEL = 6, PROF_NCLS = 8 };
 
 #define GPK_CHECK_ARG(cond, ...)        \
   do {                                  \
@@ -55,6 +59,26 @@ enum { PROF_KBUILD = 0, PROF_GEMM = 1, PROF_LEAF = 2, PROF_SKINNY = 3, PROF_MISC
     int r__ = (expr);         \
     if (r__ != 0) return r__; \
   } while (0)
+
+// One-time setup that belongs to a DEVICE (constant-memory tables, cudaFuncSetAttribute, occupancy queries): runs
+// `f` once per device under a lock, so a process that drives several GPUs initialises each of them.
+class PerDeviceOnce {
+  std::mutex mu_;
+  std::vector<char> done_;
+
+ public:
+  template <class F>
+  int run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    std::lock_guard<std::mutex> lk(mu_);
+    if ((int)done_.size() <= dev) done_.resize(dev + 1, 0);
+    if (done_[dev]) return 0;
+    const int rc = f();
+    if (rc == 0) done_[dev] = 1;
+    return rc;
+  }
+};
 
 inline size_t dtype_size(int dtype) { return dtype == GPK_F64 ? 8 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -96,14 +120,11 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
 
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
-            cudaStream_t st, bool need_dinv = true);
+            cudaStream_t st, bool need_dinv = true, double cond_hint = 0.0);
 
 // tcgen05 (int8-sliced fp64) symmetric rank-k update, gemm_tc.cu
 bool tc_enabled();
 int tc_slices();
-size_t syrk_tc_ws_bytes(int64_t m, int64_t K, int S);
-int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
-                void* ws, size_t ws_bytes, cudaStream_t st, const GemmOpts* opts = nullptr);
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype);
 
 // tcgen05 kind::tf32 (3xTF32) fp32 GEMM, gemm_tf32.cu

@@ -27,6 +27,27 @@ static inline int64_t pad_ld(int64_t n) { return (n + 3) / 4 * 4; }
 // ---------------------------------------------------------------------------------------------
 // GPR
 // ---------------------------------------------------------------------------------------------
+// Upper bound of max_i K_ii for the expression tree when every leaf has a constant diagonal (stationary, White,
+// Constant: the variance); <= 0 when a leaf's diagonal depends on x (Linear, Polynomial): unknown.
+static double diag_bound(const gpk_knode* nodes, int idx) {
+  const gpk_knode& nd = nodes[idx];
+  if (nd.op == GPK_K_SUM || nd.op == GPK_K_PRODUCT) {
+    double acc = nd.op == GPK_K_SUM ? 0.0 : 1.0;
+    for (int c = 0; c < nd.n_children; ++c) {
+      const double v = diag_bound(nodes, nd.child[c]);
+      if (!(v > 0.0)) return 0.0;
+      acc = nd.op == GPK_K_SUM ? acc + v : acc * v;
+    }
+    return acc;
+  }
+  if (nd.op == GPK_K_LINEAR || nd.op == GPK_K_POLYNOMIAL) return 0.0;
+  return nd.variance;
+}
+static double gpr_cond_hint(const gpk_knode* nodes, int n_nodes, double noise_variance) {
+  const double d = diag_bound(nodes, n_nodes - 1);
+  return (d > 0.0 && noise_variance > 0.0) ? (d + noise_variance) / noise_variance : 0.0;
+}
+
 struct GprWs {
   void* A; int64_t lda; void* dinv; int32_t* info; size_t bytes;
 };
@@ -62,7 +83,8 @@ int gpr_lml(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const doub
   char* Yrows = (char*)w.A + (size_t)N * w.lda * ts;
   GPK_TRY(transpose_impl(Yc, N, P, P, Yrows, w.lda, dtype, st));
   // alpha comes out of the factorisation itself (extra rows): no trsm on this factor, block inverses not needed
-  GPK_TRY(potrf_any(w.A, N, N + P, w.lda, dtype, w.info, w.dinv, st, /*need_dinv=*/false));  // gpr.py:102
+  GPK_TRY(potrf_any(w.A, N, N + P, w.lda, dtype, w.info, w.dinv, st, /*need_dinv=*/false,
+                    noise_vec ? 0.0 : gpr_cond_hint(nodes, n_nodes, noise_variance)));  // gpr.py:102
   GPK_CUDA_OK(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
   for (int64_t p = 0; p < P; ++p)
     GPK_TRY(reduce_impl(1, Yrows + (size_t)p * w.lda * ts, N, 1, 1.0, 1, out + 1, dtype, st));
@@ -70,6 +92,63 @@ int gpr_lml(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const doub
   gpr_finalize_kernel<<<1, 1, 0, st>>>(out, w.info, (double)N, (double)P);
   GPK_LAUNCH_OK();
   return 0;
+}
+
+// ---- value + gradient (grad.cu) -----------------------------------------------------------------
+int potri_lower(double* L, int64_t n, int64_t ldl, const double* dinv, double* Kinv, int64_t ldk, double* tmp,
+                cudaStream_t st);
+int gpr_grad_launch(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const double* X,
+                    int64_t N, int64_t ldx, int64_t D, const double* alpha, int P, const double* Kinv, int64_t ldk,
+                    double* gout, cudaStream_t st);
+
+struct GprGradWs {
+  GprWs f; void* Kinv; void* tmp; void* alpha; size_t bytes;
+};
+static GprGradWs gpr_grad_layout(void* ws, int64_t N, int64_t P, int dtype) {
+  GprGradWs w;
+  w.f = gpr_layout(ws, N, P, dtype);
+  Arena a(ws);
+  a.off = w.f.bytes;
+  const size_t ts = dtype_size(dtype);
+  const int64_t h = N / 2 + NB;
+  w.Kinv = a.take((size_t)N * w.f.lda * ts);
+  w.tmp = a.take((size_t)h * h * ts);
+  w.alpha = a.take((size_t)N * P * ts);
+  w.bytes = a.off;
+  return w;
+}
+
+size_t gpr_lml_grad_ws(int64_t N, int64_t P, int dtype) { return gpr_grad_layout(nullptr, N, P, dtype).bytes; }
+
+// out: [0..3] as gpr_lml; [4] d/dvariance, [5] d/dnoise_variance, [6 ...] d/dlengthscale (1 or n_ard entries)
+int gpr_lml_grad(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* X, int64_t N,
+                 int64_t ldx, int64_t D, const void* Yc, int64_t P, double noise_variance, int dtype, double* out,
+                 int n_out, void* ws, cudaStream_t st) {
+  GPK_CHECK_ARG(dtype == GPK_F64, "gpr_lml_grad: the device backward computes in float64");
+  GPK_CHECK_ARG(N > 0 && P > 0 && ws && out && Yc && n_out >= 7, "gpr_lml_grad: bad arguments");
+  GprGradWs w = gpr_grad_layout(ws, N, P, dtype);
+  const size_t ts = dtype_size(dtype);
+  // forward pass (gpr.py:91-107) keeping the block inverses of the factor
+  GPK_TRY(kbuild_impl(nodes, n_nodes, dims, ard, X, N, ldx, nullptr, N, ldx, D, w.f.A, w.f.lda, dtype, GPK_LOWER,
+                      noise_variance, nullptr, st));
+  char* Yrows = (char*)w.f.A + (size_t)N * w.f.lda * ts;
+  GPK_TRY(transpose_impl(Yc, N, P, P, Yrows, w.f.lda, dtype, st));
+  GPK_TRY(potrf_any(w.f.A, N, N + P, w.f.lda, dtype, w.f.info, w.f.dinv, st, /*need_dinv=*/true,
+                    gpr_cond_hint(nodes, n_nodes, noise_variance)));
+  GPK_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)n_out * sizeof(double), st));
+  for (int64_t p = 0; p < P; ++p)
+    GPK_TRY(reduce_impl(1, Yrows + (size_t)p * w.f.lda * ts, N, 1, 1.0, 1, out + 1, dtype, st));
+  GPK_TRY(reduce_impl(2, w.f.A, N, w.f.lda + 1, 1.0, 1, out + 2, dtype, st));
+  gpr_finalize_kernel<<<1, 1, 0, st>>>(out, w.f.info, (double)N, (double)P);
+  GPK_LAUNCH_OK();
+  // alpha = L^-T beta  (beta^T = the extra rows)
+  GPK_TRY(transpose_impl(Yrows, P, N, w.f.lda, w.alpha, P, dtype, st));
+  GPK_TRY(trsm_any(1, w.f.A, N, w.f.lda, w.alpha, P, P, dtype, w.f.dinv, st));
+  // K^-1 (lower) = L^-T L^-1; the factor is overwritten by its inverse
+  GPK_TRY(potri_lower((double*)w.f.A, N, w.f.lda, (const double*)w.f.dinv, (double*)w.Kinv, w.f.lda, (double*)w.tmp, st));
+  // sum G (.) dK/dtheta, G = 1/2 (alpha alpha^T - P K^-1)
+  return gpr_grad_launch(nodes, n_nodes, dims, ard, (const double*)X, N, ldx, D, (const double*)w.alpha, (int)P,
+                         (const double*)w.Kinv, w.f.lda, out + 4, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,11 +280,28 @@ __global__ void svgp_finalize_kernel(double* out, const double* scal, const int3
 
 size_t svgp_elbo_ws(int64_t B, int64_t M, int64_t P, int dtype) { return svgp_layout(nullptr, B, M, P, dtype).bytes; }
 
+// byte offset and leading dimension of A [M, ldb] inside the workspace (for the all-gather between stages 1 and 2)
+size_t svgp_elbo_A(int64_t B, int64_t M, int64_t P, int dtype, int64_t* ld) {
+  SvgpWs w = svgp_layout(nullptr, B, M, P, dtype);
+  if (ld) *ld = w.ldb;
+  return (size_t)((char*)w.A - (char*)nullptr);
+}
+
 int svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard, const void* Xb, int64_t B,
               int64_t ldx, int64_t D, const void* Yc, int64_t P, const void* Z, int64_t M, int64_t ldz,
               const void* q_mu, const void* q_sqrt, int q_diag, int whiten, double noise, double scale, double jitter,
-              int p_begin, int p_end, int dtype, double* out, void* ws, cudaStream_t st) {
+              int p_begin, int p_end, int dtype, double* out, void* ws, cudaStream_t st, int stage, int64_t c0,
+              int64_t c1) {
+  // stage 0: the whole evaluation.  Latent sharding over GPUs with a column-sharded triangular solve:
+  //   stage 1: Kuu, chol, and ONLY the columns [c0, c1) of Kuf / A = Lm^-1 Kuf (written in place in the workspace's
+  //            A [M, ldb]; gpk_svgp_elbo_A locates it) -- the caller then all-gathers the column blocks of A;
+  //   stage 2: everything after the solve for the latents [p_begin, p_end), A taken complete from the workspace.
   GPK_CHECK_ARG(B > 0 && M > 0 && P > 0 && ws && out && q_mu && q_sqrt, "svgp_elbo: bad arguments");
+  GPK_CHECK_ARG(stage >= 0 && stage <= 2, "svgp_elbo: bad stage %d", stage);
+  GPK_CHECK_ARG(stage == 0 || whiten, "svgp_elbo: the staged (column-sharded) evaluation covers whiten=True");
+  if (stage != 1) { c0 = 0; c1 = B; }
+  GPK_CHECK_ARG(0 <= c0 && c0 <= c1 && c1 <= B, "svgp_elbo: bad column range [%lld,%lld) of %lld", (long long)c0,
+                (long long)c1, (long long)B);
   GPK_CHECK_ARG(0 <= p_begin && p_begin < p_end && p_end <= P, "svgp_elbo: bad latent range [%d,%d) of %lld", p_begin,
                 p_end, (long long)P);
   GPK_CHECK_ARG(noise > 0.0, "svgp_elbo: noise variance must be positive");
@@ -215,14 +311,22 @@ int svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const do
   const char* qmu = (const char*)q_mu;
   const char* qs = (const char*)q_sqrt;
   GPK_CUDA_OK(cudaMemsetAsync(w.scal, 0, 8 * sizeof(double), st));
-  // Kmm = Kuu + jitter ; Lm = chol(Kmm)   (posteriors.py:835, util.py:67)
-  GPK_TRY(kbuild_impl(nodes, n_nodes, dims, ard, Z, M, ldz, nullptr, M, ldz, D, w.Kuu, w.ldm, dtype, GPK_LOWER, jitter,
-                      nullptr, st));
-  GPK_TRY(potrf_any(w.Kuu, M, M, w.ldm, dtype, w.info, w.dinv, st));
-  // Kmn = Kuf [M,B] ; A = Lm^-1 Kmn   (posteriors.py:836, util.py:125)
-  GPK_TRY(kbuild_impl(nodes, n_nodes, dims, ard, Z, M, ldz, Xb, B, ldx, D, w.A, w.ldb, dtype, GPK_FULL, 0.0, nullptr,
-                      st));
-  GPK_TRY(trsm_any(0, w.Kuu, M, w.ldm, w.A, B, w.ldb, dtype, w.dinv, st));
+  if (stage != 2) {
+    // Kmm = Kuu + jitter ; Lm = chol(Kmm)   (posteriors.py:835, util.py:67)
+    GPK_TRY(kbuild_impl(nodes, n_nodes, dims, ard, Z, M, ldz, nullptr, M, ldz, D, w.Kuu, w.ldm, dtype, GPK_LOWER, jitter,
+                        nullptr, st));
+    GPK_TRY(potrf_any(w.Kuu, M, M, w.ldm, dtype, w.info, w.dinv, st));
+    // Kmn = Kuf [M,B] ; A = Lm^-1 Kmn   (posteriors.py:836, util.py:125); columns [c0, c1) only in stage 1
+    if (c1 > c0) {
+      char* Ac = (char*)w.A + (size_t)c0 * ts;
+      GPK_TRY(kbuild_impl(nodes, n_nodes, dims, ard, Z, M, ldz, (const char*)Xb + (size_t)c0 * ldx * ts, c1 - c0, ldx, D,
+                          Ac, w.ldb, dtype, GPK_FULL, 0.0, nullptr, st));
+      GPK_TRY(trsm_any(0, w.Kuu, M, w.ldm, Ac, c1 - c0, w.ldb, dtype, w.dinv, st));
+    }
+    if (stage == 1) return 0;
+  } else {
+    GPK_CUDA_OK(cudaMemsetAsync(w.info, 0, sizeof(int32_t), st));
+  }
   // fvar0 = Knn - sum_m A^2   (util.py:133)
   GPK_TRY(kdiag_impl(nodes, n_nodes, dims, ard, Xb, B, ldx, D, w.v0, dtype, st));
   GPK_TRY(colsumsq_impl(w.A, M, B, w.ldb, -1.0, 1, w.v0, dtype, st));

@@ -505,14 +505,14 @@ static int launch_dmma_shape(int ta, int tb, int64_t m, int64_t n, int64_t k, do
   constexpr int ATILE = BM * DS_K > DK * (BM + 4) ? BM * DS_K : DK * (BM + 4);
   constexpr int BTILE = BN * DS_K > DK * (BN + 4) ? BN * DS_K : DK * (BN + 4);
   const size_t smem = (size_t)(2 * ATILE + 2 * BTILE) * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;  // function attributes are per device
+  GPK_TRY(attr_once.run([&]() -> int {
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+    return 0;
+  }));
   dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
   if (hf) grid = dim3(grid.y, grid.x);  // row tiles fastest: column block 0 first
   GPK_CHECK_ARG(grid.y <= 65535, "gemm: too many tiles for the grid");
@@ -559,7 +559,8 @@ int gemm_t(int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, con
   if (sizeof(T) == 4 && !hf && gemm_tf32_eligible(m, n, k, A, B, C, flags))
     return gemm_tf32(transa, transb, m, n, k, (float)alpha, (const float*)A, lda, (const float*)B, ldb, (float)beta,
                      (float*)C, ldc, flags, st);
-  ProfScope ps(PROF_GEMM, st);
+  // work = MACs the launch computes (tiles strictly above the diagonal are skipped for LOWER_ONLY: about half)
+  ProfScope ps(PROF_GEMM, st, (double)m * (double)n * (double)k * ((flags & GPK_GEMM_LOWER_ONLY) && m == n ? 0.5 : 1.0));
   if (sizeof(T) == 8 && !fp64_simt())
     return launch_dmma(transa, transb, m, n, k, (double)alpha, (const double*)A, lda, (const double*)B, ldb,
                        (double)beta, (double*)C, ldc, flags, st, hf);

@@ -25,51 +25,58 @@
 // Replaces the SYRK inside tf.linalg.cholesky (gpflow/models/gpr.py:102 etc.) for the large-K levels
 // of the recursion in potrf.cu; small-K levels and ragged shapes use the DMMA kernel of gemm.cu.
 #include "tc_common.cuh"
+#include "planes.cuh"
 
 namespace gpk {
 
-constexpr int TC_BM = 128, TC_BN = 64, TC_KB = 32;   // CTA tile, bytes (= int8 elements) per k-step
-constexpr int TC_ATILE = TC_BM * TC_KB;              // 4096 B per digit plane of an A tile
-constexpr int TC_BTILE = TC_BN * TC_KB;              // 2048 B
-constexpr int TC_MAXS = 8;
 constexpr int TC_STAGES = 4;
 constexpr int TC_TMEM_COLS = 512;
 
 // ------------------------------------------------------------------------------------------------
-// slicing pre-pass: one warp per row
+// scales and slicing
 // ------------------------------------------------------------------------------------------------
-// byte offset of element (row r in [0,128), k in [0,32)) inside one digit-plane tile:
-// canonical no-swizzle K-major UMMA layout ((8,n),2):((1,SBO),LBO) in 16-byte units, LBO=8, SBO=16
-__device__ __host__ __forceinline__ int tc_tile_off(int r, int k) {
-  return (r >> 3) * 256 + (k >> 4) * 128 + (r & 7) * 16 + (k & 15);
+// static row scales from the ORIGINAL diagonal (planes.cuh): rowscale[i] = 2^(e_i - 6), sqrt(A_ii) < 2^e_i
+__global__ void row_exp_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int64_t npad,
+                               double* __restrict__ rowscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  double sc = 0.0;
+  if (i < n) {
+    const double d = A[i * lda + i];
+    int e = 0;
+    if (d > 0.0 && d < 1e300) e = ilogb(sqrt(d)) + 1;
+    sc = scalbn(1.0, e - 6);
+  }
+  rowscale[i] = sc;
 }
 
+// dynamic slicing, one warp per row: rows [row0, row0 + nrows) of the k-range [k0, k0 + K) get the scale of their
+// running maximum over that range (the extra rows below the square part; every row when GPK_TC_STATIC=0)
 __global__ void __launch_bounds__(256)
-slice_rows_kernel(const double* __restrict__ P, int64_t m, int64_t mpad, int64_t K, int64_t ld, int S,
-                  int8_t* __restrict__ tiles, double* __restrict__ rowscale) {
+slice_rows_kernel(const double* __restrict__ P, int64_t ld, int64_t row0, int64_t nrows, int64_t k0, int64_t K,
+                  TcPlanes pl) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= mpad) return;
-  const int KB = (int)(K / TC_KB);
-  const int64_t rb = r >> 7;
-  const int rr = (int)(r & 127);
-  int8_t* rowbase = tiles + (size_t)rb * KB * S * TC_ATILE;
-  const bool live = r < m;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= nrows) return;
+  const int64_t r = row0 + i;
+  const int S = pl.S;
+  const double* src = P + i * ld;
   double mx = 0.0;
-  if (live)
-    for (int64_t k = lane; k < K; k += 32) mx = fmax(mx, fabs(P[r * ld + k]));
+  for (int64_t k = lane; k < K; k += 32) mx = fmax(mx, fabs(src[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
   if (mx > 0.0 && mx < 1e300) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
   const double sc = scalbn(1.0, -e + 6);          // x * 2^-e * 2^6
-  if (lane == 0) rowscale[r] = live ? scalbn(1.0, e - 6) : 0.0;
+  if (lane == 0) pl.rowscale[r] = scalbn(1.0, e - 6);
+  int8_t* rowbase = pl.tile(r >> 7, k0 / TC_KB);
+  const int rr = (int)(r & 127);
   // each lane converts 4 consecutive k per iteration -> one 32-bit store per digit plane
-  for (int64_t k0 = lane * 4; k0 < K; k0 += 128) {
+  for (int64_t kq = lane * 4; kq < K; kq += 128) {
     double v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = live ? P[r * ld + k0 + q] * sc : 0.0;
-    const int kb = (int)(k0 / TC_KB), kk = (int)(k0 % TC_KB);
+    for (int q = 0; q < 4; ++q) v[q] = src[kq + q] * sc;
+    const int kb = (int)(kq / TC_KB), kk = (int)(kq % TC_KB);
     int8_t* tb = rowbase + (size_t)kb * S * TC_ATILE + tc_tile_off(rr, kk);
     for (int s = 0; s < S; ++s) {
       uint32_t w = 0;
@@ -91,8 +98,10 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
          (1ull << 46);
 }
 // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
-constexpr uint32_t TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                              ((uint32_t)(TC_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc_n(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+constexpr uint32_t TC_IDESC = tc_idesc_n(TC_BN);
 
 struct TcTileIter {  // identical enumeration in every warp role
   // Work unit = CL horizontally adjacent tiles (tm, tnb .. tnb+CL-1), one per CTA of a cluster, so the
@@ -139,10 +148,14 @@ struct TcTileIter {  // identical enumeration in every warp role
   }
 };
 
-template <int S, bool TS, int CL>
+template <int S, bool TS, int CL, bool CAT>
 __global__ void __launch_bounds__(192, 1)
-syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rowscale, double* __restrict__ C,
-               int64_t ldc, int64_t m, int64_t n, int KB, int lower, int* err, int* head_flag) {
+syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int KB,
+               int lower, int* head_flag) {
+  // rows of C = global rows 128 rb0 + ..., columns of C = the same rows (C is the block right of the k-range
+  // [32 kb0, 32 (kb0 + KB)) on the diagonal); operands come from the digit-plane store (planes.cuh)
+  const double* __restrict__ rowscale = pl.rowscale + rb0 * TC_BM;
+  int* err = pl.err;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
   uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE);
@@ -181,9 +194,9 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
     TcTileIter it(m, n, lower, CL, rank);
     uint32_t st = 0, ph = 0;
     while (it.next()) {
-      const int8_t* a_src = tiles + (size_t)it.tm * KB * S * TC_ATILE;
+      const int8_t* a_src = pl.tile(rb0 + it.tm, kb0);
       const int64_t tl = it.tn_load();
-      const int8_t* b_src = tiles + (size_t)(tl >> 1) * KB * S * TC_ATILE + (tl & 1) * TC_BTILE;
+      const int8_t* b_src = pl.tile(rb0 + (tl >> 1), kb0) + (tl & 1) * TC_BTILE;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(empty0 + 8 * st, ph ^ 1, err, 101);
         if (elect_one()) {
@@ -231,19 +244,44 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
             const uint32_t a_tm = tmem_base + (uint32_t)S * TC_BN;
 #pragma unroll
             for (int s = 0; s < S; ++s) tc_cp_128x256b(a_tm + s * 8, ad0 + (uint64_t)(s * (TC_ATILE >> 4)));
+            if (CAT) {
+              // the S-s digit products of A plane s share the A operand and write ADJACENT accumulators, and the B planes
+              // are contiguous in shared memory with the same 8-row-group stride: one MMA with N = 64 (S-s) (split at
+              // 256) replaces S-s MMAs with N = 64 -- 10 instructions per k-step instead of 28 for S = 7
 #pragma unroll
-            for (int s = 0; s < S; ++s)
+              for (int s = 0; s < S; ++s)
 #pragma unroll
-              for (int t = 0; t + s < S; ++t)
-                tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
-                             TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+                for (int t = 0; t + s < S; t += 4) {
+                  const int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
+                               tc_idesc_n(TC_BN * c), (kb > 0 || s > 0) ? 1u : 0u);
+                }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int t = 0; t + s < S; ++t)
+                  tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
+                               TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+            }
           } else {
+            if (CAT) {
 #pragma unroll
-            for (int s = 0; s < S; ++s)
+              for (int s = 0; s < S; ++s)
 #pragma unroll
-              for (int t = 0; t + s < S; ++t)
-                tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
-                          bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+                for (int t = 0; t + s < S; t += 4) {
+                  const int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
+                            bd0 + (uint64_t)(t * (TC_BTILE >> 4)), tc_idesc_n(TC_BN * c), (kb > 0 || s > 0) ? 1u : 0u);
+                }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int t = 0; t + s < S; ++t)
+                  tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
+                            bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+            }
           }
           // frees the stage (in every CTA of the cluster) once these copies / MMAs have read it
           if (CL == 1) tc_commit(empty0 + 8 * st); else tc_commit_mc(empty0 + 8 * st, cl_mask);
@@ -316,17 +354,13 @@ syrk_i8_kernel(const int8_t* __restrict__ tiles, const double* __restrict__ rows
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-size_t syrk_tc_ws_bytes(int64_t m, int64_t K, int S) {
-  const int64_t mpad = (m + TC_BM - 1) / TC_BM * TC_BM;
-  return align_up((size_t)mpad * K * S, 256) + align_up((size_t)mpad * sizeof(double), 256) + 256;
-}
-
+// GPK_TC_SLICES pins the number of digit planes (6..8); 0 = chosen per factorisation (potrf.cu::pick_slices)
 int tc_slices() {
   static int s = -1;
   if (s < 0) {
     const char* e = getenv("GPK_TC_SLICES");
-    s = e ? atoi(e) : 7;
-    if (s < 6) s = 6;
+    s = e ? atoi(e) : 0;
+    if (s != 0 && s < 6) s = 6;
     if (s > TC_MAXS) s = TC_MAXS;
   }
   return s;
@@ -341,6 +375,59 @@ bool tc_enabled() {
   return v == 1;
 }
 
+static bool tc_static_scales() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_TC_STATIC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static bool tc_rect() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_TC_RECT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static size_t tc_tiles_total(int64_t rbt, int64_t nbk) {
+  return (size_t)(tc_rect() ? rbt * 4 * nbk : plane_prefix(rbt, nbk));
+}
+
+size_t tc_planes_bytes(int64_t n, int64_t rows) {
+  const int64_t nbk = (n + TC_BM - 1) / TC_BM, rbt = (rows + TC_BM - 1) / TC_BM;
+  return align_up(tc_tiles_total(rbt, nbk) * TC_MAXS * TC_ATILE, 256) + align_up((size_t)rbt * TC_BM * sizeof(double), 256) + 256;
+}
+
+TcPlanes tc_planes_layout(void* ws, int64_t n, int64_t rows, int S) {
+  const int64_t nbk = (n + TC_BM - 1) / TC_BM, rbt = (rows + TC_BM - 1) / TC_BM;
+  TcPlanes pl;
+  pl.planes = (int8_t*)ws;
+  pl.rowscale = (double*)((char*)ws + align_up(tc_tiles_total(rbt, nbk) * TC_MAXS * TC_ATILE, 256));
+  pl.rect = tc_rect();
+  pl.err = (int*)((char*)pl.rowscale + align_up((size_t)rbt * TC_BM * sizeof(double), 256));
+  pl.S = S;
+  pl.nbk = nbk;
+  pl.n_sq = n;
+  pl.is_static = tc_static_scales();
+  return pl;
+}
+
+int tc_row_exponents(const double* A, int64_t lda, const TcPlanes& pl, cudaStream_t st) {
+  const int64_t npad = (pl.n_sq + TC_BM - 1) / TC_BM * TC_BM;
+  ProfScope ps(PROF_MISC, st);
+  row_exp_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(A, lda, pl.n_sq, npad, pl.rowscale);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
+int tc_slice_rows(const double* P, int64_t ld, int64_t row0, int64_t nrows, int64_t k0, int64_t K, const TcPlanes& pl,
+                  cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  GPK_CHECK_ARG(K % TC_KB == 0 && k0 % TC_KB == 0, "tc_slice_rows: k-range must be a multiple of 32");
+  ProfScope ps(PROF_MISC, st);
+  slice_rows_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(P, ld, row0, nrows, k0, K, pl);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+
 static int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -352,27 +439,22 @@ static int tc_num_sms() {
   return n;
 }
 
-// C[m,n] -= A[m,K] A[0:n,K]^T (lower tiles only if `lower`); K % 32 == 0, n <= m.
-int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, int64_t K, int lower,
-                void* ws, size_t ws_bytes, cudaStream_t st, const GemmOpts* opts) {
-  const int S = tc_slices();
+// C[m,n] -= L[r0:r0+m, k0:k0+K] L[r0:r0+n, k0:k0+K]^T (lower tiles only if `lower`); K, k0 % 32 == 0, r0 % 128 == 0, n <= m.
+int syrk_tc_planes(double* C, int64_t ldc, int64_t m, int64_t n, const TcPlanes& pl, int64_t r0, int64_t k0, int64_t K,
+                   int lower, cudaStream_t st, const GemmOpts* opts) {
+  const int S = pl.S;
   int* hf = opts ? opts->head_flag : nullptr;
-  GPK_CHECK_ARG(K % TC_KB == 0 && K > 0 && n <= m, "syrk_tc: unsupported shape m=%lld n=%lld K=%lld", (long long)m,
-                (long long)n, (long long)K);
-  GPK_CHECK_ARG(ws && ws_bytes >= syrk_tc_ws_bytes(m, K, S), "syrk_tc: workspace too small");
-  const int64_t mpad = (m + TC_BM - 1) / TC_BM * TC_BM;
-  int8_t* tiles = (int8_t*)ws;
-  double* rowscale = (double*)((char*)ws + align_up((size_t)mpad * K * S, 256));
-  int* err = (int*)((char*)rowscale + align_up((size_t)mpad * sizeof(double), 256));
-  {
-    ProfScope ps(PROF_MISC, st);
-    slice_rows_kernel<<<(unsigned)((mpad + 7) / 8), 256, 0, st>>>(A, m, mpad, K, lda, S, tiles, rowscale);
-    GPK_LAUNCH_OK();
-  }
+  GPK_CHECK_ARG(K % TC_KB == 0 && K > 0 && n <= m && r0 % TC_BM == 0 && k0 % TC_KB == 0,
+                "syrk_tc: unsupported shape m=%lld n=%lld K=%lld r0=%lld k0=%lld", (long long)m, (long long)n, (long long)K,
+                (long long)r0, (long long)k0);
+  const int64_t rb0 = r0 / TC_BM, kb0 = k0 / TC_KB;
   const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
-  // A planes through TMEM (tcgen05.cp + TS-form MMA) by default; GPK_TC_A_TMEM=0 selects the SS form.
+  // Both operands from shared memory with the digit products of one A plane CONCATENATED along N (one MMA of N up to 256
+  // instead of up to four of N = 64): scripts/mb_mma.cu measures 52.9 cycles per N = 64 SS MMA against a floor of 32,
+  // but 128.0 per N = 256 MMA (= the floor), and the tcgen05.cp of the TS form costs 137 cycles per k-step on top.
+  // C2: 8.70 ms (TS, N = 64) -> 8.14 ms (SS, concatenated).  GPK_TC_A_TMEM=1 / GPK_TC_CAT=0 select the older forms.
   // Clusters of 2 CTAs multicast the shared A tile (the kernel is L2->SM bandwidth bound); GPK_TC_CLUSTER=1 disables.
-  static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return !(e && e[0] == '0'); }();
+  static const bool ts = []() { const char* e = getenv("GPK_TC_A_TMEM"); return e && e[0] == '1'; }();
   static const int cl = []() {
     const char* e = getenv("GPK_TC_CLUSTER");
     return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : 2;
@@ -388,8 +470,9 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
   grid = grid / cl * cl;
   if (nunits * cl < grid) grid = (int)(nunits * cl);
   if (grid < 1) return 0;
-  ProfScope ps(PROF_GEMM, st);
   const int KBn = (int)(K / TC_KB);
+  // issued int8 MACs: every tile of every unit (padding tiles included) x k-steps x S(S+1)/2 digit products
+  ProfScope ps(PROF_TC, st, (double)nunits * cl * KBn * (S * (S + 1) / 2) * (double)(TC_BM * TC_BN * TC_KB));
   auto launch = [&](auto kern) -> int {
     static_cast<void>(0);
     GPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -405,23 +488,26 @@ int syrk_tc_f64(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, i
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const int8_t*)tiles, (const double*)rowscale, C, ldc, m, n, KBn, lower, err, hf));
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, pl, rb0, kb0, C, ldc, m, n, KBn, lower, hf));
     count_launch();
     return 0;
   };
+  static const bool cat = []() { const char* e = getenv("GPK_TC_CAT"); return !(e && e[0] == '0'); }();
+#define GPK_TC_PICK(SS, TT, CC) (cat ? launch(syrk_i8_kernel<SS, TT, CC, true>) : launch(syrk_i8_kernel<SS, TT, CC, false>))
   if (cl == 4) {
-    if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 4>) : launch(syrk_i8_kernel<6, false, 4>);
-    if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 4>) : launch(syrk_i8_kernel<7, false, 4>);
-    return launch(syrk_i8_kernel<8, false, 4>);
+    if (S == 6) return ts ? GPK_TC_PICK(6, true, 4) : GPK_TC_PICK(6, false, 4);
+    if (S == 7) return ts ? GPK_TC_PICK(7, true, 4) : GPK_TC_PICK(7, false, 4);
+    return GPK_TC_PICK(8, false, 4);
   }
   if (cl == 2) {
-    if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 2>) : launch(syrk_i8_kernel<6, false, 2>);
-    if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 2>) : launch(syrk_i8_kernel<7, false, 2>);
-    return launch(syrk_i8_kernel<8, false, 2>);
+    if (S == 6) return ts ? GPK_TC_PICK(6, true, 2) : GPK_TC_PICK(6, false, 2);
+    if (S == 7) return ts ? GPK_TC_PICK(7, true, 2) : GPK_TC_PICK(7, false, 2);
+    return GPK_TC_PICK(8, false, 2);
   }
-  if (S == 6) return ts ? launch(syrk_i8_kernel<6, true, 1>) : launch(syrk_i8_kernel<6, false, 1>);
-  if (S == 7) return ts ? launch(syrk_i8_kernel<7, true, 1>) : launch(syrk_i8_kernel<7, false, 1>);
-  return launch(syrk_i8_kernel<8, false, 1>);
+  if (S == 6) return ts ? GPK_TC_PICK(6, true, 1) : GPK_TC_PICK(6, false, 1);
+  if (S == 7) return ts ? GPK_TC_PICK(7, true, 1) : GPK_TC_PICK(7, false, 1);
+  return GPK_TC_PICK(8, false, 1);
+#undef GPK_TC_PICK
 }
 
 }  // namespace gpk

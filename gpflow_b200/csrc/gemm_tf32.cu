@@ -437,15 +437,15 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   }
   if ((flags & GPK_GEMM_COLSUMSQ) && nsplit > 1) nsplit = 1;  // sums of squares need the complete dot products
   const size_t smem = (size_t)TF_STAGES * TF_STAGE_BYTES + 2 * TF_EPI_BYTES + 256;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;  // function attributes are per device
+  GPK_TRY(attr_once.run([&]() -> int {
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPK_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+    return 0;
+  }));
   int grid = (int)std::min<int64_t>(sms / cl * cl, nunits * cl * nsplit);
   const int tri = (flags & GPK_GEMM_A_LOWER) ? (transa ? 2 : 1) : 0;
-  ProfScope ps(PROF_GEMM, st);
+  ProfScope ps(PROF_TC, st, 3.0 * (double)m * (double)n * (double)k * (tri ? 0.5 : 1.0));  // tf32 MACs issued (3xTF32)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TF_THREADS);

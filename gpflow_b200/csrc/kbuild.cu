@@ -386,7 +386,6 @@ __global__ void kdiag_kernel(const __grid_constant__ KProg prog, const T* __rest
 // =============================================================================================
 __constant__ double c_exp2_tab[64];
 static double h_exp2_tab[64];
-static bool h_exp2_tab_ready = false;
 
 // The fast path works on x = c * r2 (c folded into the per-dimension weights on the host together with the
 // 1/lengthscale^2 scale): RBF c = 1/2 (k = v exp(-x)), Matern12 c = 1 (u = sqrt x, k = v exp(-u)),
@@ -759,14 +758,16 @@ static int kbuild_fast_go(const KProg& p, const void* X, int64_t N, int64_t ldx,
                           cudaStream_t st) {
   const int64_t nty = (N + KB_TILE - 1) / KB_TILE, ntx = (N2 + KB_TILE - 1) / KB_TILE;
   const int64_t ntiles = mode == 0 ? nty * ntx : nty * (nty + 1) / 2;
-  static int grid_max = 0;  // persistent grid: resident CTAs per SM x SM count
-  if (!grid_max) {
+  static int grid_max = 0;  // persistent grid: resident CTAs per SM x SM count (the same on every B200 of a box)
+  static PerDeviceOnce once;
+  GPK_TRY(once.run([&]() -> int {
     int dev = 0, sms = 0, per_sm = 0;
     GPK_CUDA_OK(cudaGetDevice(&dev));
     GPK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     GPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kbuild_fast_kernel<T, TYPE, MINB>, 256, 0));
     grid_max = sms * (per_sm > 0 ? per_sm : 1);
-  }
+    return 0;
+  }));
   const int64_t grid = ntiles < grid_max ? ntiles : grid_max;
   kbuild_fast_kernel<T, TYPE, MINB><<<(unsigned)grid, 256, 0, st>>>(p, (const T*)X, N, ldx, (const T*)X2, N2, ldx2, (T*)K, ldk,
                                                                mode, (T)diag_scalar, (const T*)diag_vec, vec_ok, ntiles);
@@ -778,11 +779,12 @@ template <typename T>
 static int kbuild_fast_launch(const KProg& p, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2,
                               int64_t ldx2, void* K, int64_t ldk, int lower, double diag_scalar, const void* diag_vec,
                               cudaStream_t st) {
-  if (!h_exp2_tab_ready) {
+  static PerDeviceOnce tab_once;  // __constant__ symbols live per device
+  GPK_TRY(tab_once.run([&]() -> int {
     for (int j = 0; j < 64; ++j) h_exp2_tab[j] = exp2((double)j / 64.0);
     GPK_CUDA_OK(cudaMemcpyToSymbol(c_exp2_tab, h_exp2_tab, sizeof(h_exp2_tab)));
-    h_exp2_tab_ready = true;
-  }
+    return 0;
+  }));
   ProfScope ps(PROF_KBUILD, st);
   const int vec_ok = ((uintptr_t)K % 16 == 0) && ((ldk * sizeof(T)) % 16 == 0);
   const int mode = p.symmetric ? (lower ? 1 : 2) : 0;

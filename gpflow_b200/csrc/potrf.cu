@@ -22,6 +22,7 @@
 #include <utility>
 
 #include "common.cuh"
+#include "planes.cuh"
 
 namespace gpk {
 
@@ -457,9 +458,28 @@ __device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// Optional extras of the panel kernel (both off = the plain solve):
+//  * PanelEmit: the finished rows are also written as int8 digit planes into the plane store (planes.cuh), with the
+//    static row scales -- this replaces the slicing pass over L in front of every tcgen05 update;
+//  * PanelFuse: the K = 128 trailing update of the NEXT block column, C[rows, 0:uc] -= X X_top^T with X_top = the first
+//    `uc` solved rows (they belong to the first two CTAs, which publish them through a counter), is applied by the same
+//    CTA while X is still in shared memory; CTAs holding rows of the next diagonal block report them to the look-ahead
+//    counter, so the next leaf starts while the rest of the grid is still updating.
+struct PanelEmit {
+  TcPlanes pl;        // pl.planes == nullptr: off
+  int64_t row_g0;     // global row index of B's first row
+  int64_t col_g0;     // global column index of the block
+};
+struct PanelFuse {
+  double* C;          // nullptr: off.  C[rows, uc] (same rows as B), leading dimension ldb
+  int uc;             // columns of the update (<= 128)
+  int* flag;          // [1]: 32x32 units of the next diagonal block done, [2]: X_top CTAs finished
+  int64_t mu, nu;     // shape of the whole update (rows, uc) for diag_units_tile
+};
+
 __global__ void __launch_bounds__(256, 1)
 potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const double* __restrict__ Lblk, int64_t ldl,
-                   int nb, const double* __restrict__ dinv64) {
+                   int nb, const double* __restrict__ dinv64, PanelEmit em, PanelFuse fu) {
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   double* Bs = reinterpret_cast<double*>(leaf_smem);  // [64][PLB]
   double* Ai = Bs + PR * PLB;                          // [64][PLW]  A^-1
@@ -544,9 +564,111 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
       }
     }
   }
+  // ---- fused K = nb update of the next block column: X_top published first (everybody needs it)
+  if (fu.C) {
+    const int ntop = (fu.uc + PR - 1) / PR;  // CTAs that own rows of X_top
+    __syncthreads();                         // all warps' rows are in global memory
+    if ((int)blockIdx.x < ntop && tid == 0) {
+      __threadfence();
+      atomicAdd(fu.flag + 2, 1);
+    }
+  }
+  // ---- digit planes of the finished rows (static scales; the extra rows below the square part are sliced elsewhere)
+  if (em.pl.planes && nb == NB) {
+    const int S = em.pl.S;
+#pragma unroll 1
+    for (int rr = 0; rr < 8; ++rr) {
+      const int64_t row = r0 + w * 8 + rr, grow = em.row_g0 + row;
+      if (row < rows && grow < em.pl.n_sq) {
+        const double inv = 1.0 / em.pl.rowscale[grow];  // exact: a power of two
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = Bw[rr * PLB + lane * 4 + u] * inv;
+        const int64_t kcol = em.col_g0 + lane * 4;
+        int8_t* tb = em.pl.tile(grow >> 7, kcol / TC_KB) + tc_tile_off((int)(grow & 127), (int)(kcol % TC_KB));
+        for (int s2 = 0; s2 < S; ++s2) {
+          uint32_t wd = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double d = rint(v[u]);
+            v[u] = (v[u] - d) * 128.0;
+            wd |= (uint32_t)((int)d & 0xff) << (8 * u);
+          }
+          *reinterpret_cast<uint32_t*>(tb + (size_t)s2 * TC_ATILE) = wd;
+        }
+      }
+    }
+  }
+  if (!fu.C) return;
+  // ---- C[own rows, 0:uc] -= X[own rows, 0:nb] X_top[0:uc, 0:nb]^T
+  {
+    const int ntop = (fu.uc + PR - 1) / PR;
+    double* Xt = Ai;  // [128][PLB] staged X_top: reuses the operand area (everybody passed the barrier above)
+    if (tid == 0) {
+      unsigned spins = 0;
+      while (atomicAdd(fu.flag + 2, 0) < ntop) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    // (L2 loads: the rows were written by other CTAs of this grid)
+    if ((ldb & 1) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) {
+      for (int e = tid; e < NB * 64; e += 256) {  // 128 rows x 64 double2
+        const int i = e >> 6, c2 = (e & 63) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (i < fu.uc) v = __ldcg(reinterpret_cast<const double2*>(B + (int64_t)i * ldb + c2));
+        *reinterpret_cast<double2*>(Xt + i * PLB + c2) = v;
+      }
+    } else {
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, c = e & 127;
+        Xt[i * PLB + c] = i < fu.uc ? __ldcg(B + (int64_t)i * ldb + c) : 0.0;
+      }
+    }
+    // accumulators = this warp's 8 rows of C (DMMA C-fragment layout: row g, columns 8 cb + 2q, +1)
+    const int64_t crow = r0 + w * 8 + g;
+    double cacc[16][2];
+#pragma unroll
+    for (int cb = 0; cb < 16; ++cb) {
+      const int c = cb * 8 + 2 * q;
+      cacc[cb][0] = (crow < rows && c < fu.uc) ? fu.C[crow * ldb + c] : 0.0;
+      cacc[cb][1] = (crow < rows && c + 1 < fu.uc) ? fu.C[crow * ldb + c + 1] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {  // two halves of k keep the A fragments at 16 registers
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) af[ks] = -Bw[g * PLB + kh * 64 + ks * 4 + q];
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+        for (int cb = 0; cb < 16; ++cb) dmma884p(cacc[cb], af[ks], Xt[(cb * 8 + g) * PLB + kh * 64 + ks * 4 + q]);
+    }
+    if (crow < rows) {
+#pragma unroll
+      for (int cb = 0; cb < 16; ++cb) {
+        const int c = cb * 8 + 2 * q;
+        if (c < fu.uc) fu.C[crow * ldb + c] = cacc[cb][0];
+        if (c + 1 < fu.uc) fu.C[crow * ldb + c + 1] = cacc[cb][1];
+      }
+    }
+    // look-ahead: rows of the next diagonal block are complete
+    const int u = diag_units_tile(r0, 0, PR, NB, fu.mu, fu.nu);
+    if (u) {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(fu.flag + 1, u);
+      }
+    }
+  }
 }
 
-static size_t panel_smem_bytes() { return (size_t)(PR * PLB + 3 * 64 * PLW) * sizeof(double); }
+static size_t panel_smem_bytes(bool fused = false) {
+  return (size_t)(PR * PLB + (fused ? NB * PLB : 3 * 64 * PLW)) * sizeof(double);
+}
 
 // ---- standalone inverse of the diagonal blocks of a given factor (for trsm without cached dinv) -----
 template <typename T>
@@ -573,19 +695,18 @@ static size_t leaf_smem_bytes() { return (size_t)(NB * LS + NB + 4096) * sizeof(
 
 template <typename T>
 static int leaf_attr() {
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;  // function attributes are per device
+  return once.run([&]() -> int {
     GPK_CUDA_OK(cudaFuncSetAttribute(potrf_leaf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)leaf_smem_bytes<T>()));
     GPK_CUDA_OK(cudaFuncSetAttribute(potrf_leaf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)leaf_smem_bytes<T>()));
     GPK_CUDA_OK(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)panel_smem_bytes()));
+                                     (int)panel_smem_bytes(true)));
     GPK_CUDA_OK(cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)leaf_smem_bytes<T>()));
-    done = true;
-  }
-  return 0;
+    return 0;
+  });
 }
 
 static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
@@ -604,16 +725,24 @@ static int64_t tc_min_k() {
 struct LookAhead {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_inputs = nullptr, ev_side = nullptr, ev_u = nullptr;
-  int* flag = nullptr;     // device counters (in the workspace): [0] head tiles done, [1] diagonal tiles done
+  int* flag = nullptr;     // device counters (in the workspace): [0] head tiles done, [1] diagonal units done, [2] X_top CTAs
   int target = 0;
   bool pending = false;
   bool enabled = false;
   bool slim = false;       // fp64, n > 128: slim leaves + potrf_panel_kernel (full block inverses filled in afterwards)
+  bool fuse = false;       // slim + look-ahead: the K = 128 updates are applied by the panel kernel itself
+  TcPlanes pl;             // digit-plane store of this factorisation (pl.planes == nullptr: tcgen05 updates off)
 };
 
 static bool lookahead_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPK_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static bool fuse_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_PANEL_FUSE"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -643,16 +772,23 @@ static int lookahead_init(LookAhead& la, int* flag, cudaStream_t st) {
   return 0;
 }
 
+// C = A[col0 + n1 :, col0 + n1 : col0 + n] -= P P[0 : n - n1]^T with P = the finished columns [col0, col0 + K) below
 template <typename T>
-static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, void* tcws,
-                           size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
+static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, int64_t col0,
+                           LookAhead& la, cudaStream_t st) {
   GemmOpts opts;
   // int32 accumulators: 64 * 64 * K * S < 2^31 (tests/test_digit_slicing_model.py); deeper updates use DMMA
-  const bool use_tc = sizeof(T) == 8 && tcws && tc_enabled() && K >= tc_min_k() && K % 32 == 0 && n <= m &&
-                      K * tc_slices() * 4096 < (1ll << 31) &&
-                      tcws_bytes >= syrk_tc_ws_bytes(m, K, tc_slices());
+  const bool use_tc = sizeof(T) == 8 && la.pl.planes && K >= tc_min_k() && K % 32 == 0 && n <= m &&
+                      K * la.pl.S * 4096 < (1ll << 31);
+  if (use_tc) {
+    // operand rows without a static scale: the extra rows below the square part (or every row, GPK_TC_STATIC=0)
+    const int64_t r0 = col0 + K;
+    const int64_t dyn0 = la.pl.is_static ? (la.pl.n_sq > r0 ? la.pl.n_sq : r0) : r0;
+    if (dyn0 < r0 + m)
+      GPK_TRY(tc_slice_rows((const double*)P + (dyn0 - r0) * ldp, ldp, dyn0, r0 + m - dyn0, col0, K, la.pl, st));
+  }
   if (la.enabled) {
-    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 2 * sizeof(int), st));
+    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));
     opts.head_flag = la.flag;
     la.target = diag_units_total(m, n);  // 32x32 units of the next 128x128 diagonal block
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
@@ -660,7 +796,7 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
   }
   int rc;
   if (use_tc)
-    rc = syrk_tc_f64((double*)C, ldc, m, n, (const double*)P, ldp, K, 1, tcws, tcws_bytes, st, &opts);
+    rc = syrk_tc_planes((double*)C, ldc, m, n, la.pl, col0 + K, col0, K, 1, st, &opts);
   else
     rc = gemm_t<T>(0, 1, m, n, K, T(-1), P, ldp, P, ldp, T(1), C, ldc, GPK_GEMM_LOWER_ONLY, st, &opts);
   if (rc == 0 && la.enabled) GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));  // U complete
@@ -669,56 +805,106 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
 
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
   if (dtype != GPK_F64 || n < 2 * 128) return 0;  // sized for any GPK_TC_MIN_K >= 128
-  return syrk_tc_ws_bytes(rows, ((n / NB + 1) / 2) * NB, 8);
+  return tc_planes_bytes(n, rows);
 }
 
+// One diagonal block (n <= 128) at global column col0: leaf, then the rows below.  fuse_cols > 0: the panel kernel
+// also applies the K = n update of the next fuse_cols columns (the caller skips that trailing update).
 template <typename T>
-static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, void* tcws,
-                     size_t tcws_bytes, LookAhead& la, cudaStream_t st) {
-  if (n <= NB) {
-    T* dblk = dinv + (size_t)(col0 / NB) * NB * NB;
-    // look-ahead: run the leaf (and its panel solve) on the side stream, gated by U's head-tile counter
-    cudaStream_t ls = st;
-    int* wf = nullptr;
-    int wt = 0;
-    if (la.pending) {
-      GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_inputs, 0));
-      ls = la.side;
-      wf = la.flag + 1;  // the leaf needs only the diagonal block of U's output
-      wt = la.target;
-    }
-    {
-      ProfScope ps(PROF_LEAF, ls);
-      if (la.slim)
-        potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
-      else
-        potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
-      GPK_LAUNCH_OK();
-    }
-    if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
-    if (rows > n) {  // rows below: X = B L^-T, in place
-      if (la.slim) {
-        ProfScope ps(PROF_GEMM, ls);
-        const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
-        potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(), ls>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
-                                                                   (int)n, (const double*)dblk);
-        GPK_LAUNCH_OK();
-      } else {  // one GEMM with the block inverse (single column tile)
-        GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, ls));
-      }
-    }
+static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, int fuse_cols,
+                       LookAhead& la, cudaStream_t st) {
+  T* dblk = dinv + (size_t)(col0 / NB) * NB * NB;
+  // look-ahead: run the leaf (and its panel solve) on the side stream, gated by U's head-tile counter
+  cudaStream_t ls = st;
+  int* wf = nullptr;
+  int wt = 0;
+  if (la.pending) {
+    GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_inputs, 0));
+    ls = la.side;
+    wf = la.flag + 1;  // the leaf needs only the diagonal block of U's output
+    wt = la.target;
+  }
+  {
+    ProfScope ps(PROF_LEAF, ls);
+    if (la.slim)
+      potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+    else
+      potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+    GPK_LAUNCH_OK();
+  }
+  if (rows <= n) {
     if (la.pending) {
       GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
-      GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));  // main stream joins (it also still holds U)
+      GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));
       la.pending = false;
     }
     return 0;
   }
+  PanelEmit em{};
+  PanelFuse fu{};
+  if (la.slim && la.pl.is_static) {  // (GPK_TC_STATIC=0: every update slices its own operand rows instead)
+    em.pl = la.pl;
+    em.row_g0 = col0 + n;
+    em.col_g0 = col0;
+  }
+  if (la.slim && fuse_cols > 0) {
+    // The fused panel + update plays the role of U: it runs on the MAIN stream (behind the previous U, which it needs
+    // completely), publishes the next diagonal block through the counter and the next leaf overlaps it on the side stream.
+    if (la.pending) {
+      GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
+      GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));
+      la.pending = false;
+    }
+    fu.C = (double*)(A + n * lda + n);
+    fu.uc = fuse_cols;
+    fu.flag = la.flag;
+    fu.mu = rows - n;
+    fu.nu = fuse_cols;
+    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));
+    la.target = diag_units_total(rows - n, fuse_cols);
+    GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
+    la.pending = true;
+    {
+      ProfScope ps(PROF_PANEL, st);
+      const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
+      potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(true), st>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
+                                                                     (int)n, (const double*)dblk, em, fu);
+      GPK_LAUNCH_OK();
+    }
+    GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));
+    return 0;
+  }
+  if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
+  if (la.slim) {
+    ProfScope ps(PROF_PANEL, ls);
+    const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
+    potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(), ls>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
+                                                               (int)n, (const double*)dblk, em, fu);
+    GPK_LAUNCH_OK();
+  } else {  // one GEMM with the block inverse (single column tile)
+    GPK_TRY(gemm_t<T>(0, 1, rows - n, n, n, T(1), A + n * lda, lda, dblk, NB, T(0), A + n * lda, lda, 0, ls));
+  }
+  if (la.pending) {
+    GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
+    GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));  // main stream joins (it also still holds U)
+    la.pending = false;
+  }
+  return 0;
+}
+
+template <typename T>
+static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, LookAhead& la,
+                     cudaStream_t st) {
+  if (n <= NB) return potrf_block<T>(A, n, rows, lda, info, dinv, col0, 0, la, st);
   const int64_t n1 = split_point(n);
-  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, tcws, tcws_bytes, la, st));
+  if (n <= 2 * NB && la.fuse) {  // two diagonal blocks: the K = 128 update between them is fused into the first panel
+    GPK_TRY(potrf_block<T>(A, n1, rows, lda, info, dinv, col0, (int)(n - n1), la, st));
+    return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st);
+  }
+  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, la, st));
   // trailing update: A[n1:rows, n1:n] -= A[n1:rows, :n1] A[n1:n, :n1]^T  (lower tiles only)
-  GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, tcws, tcws_bytes, la, st));
-  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, tcws, tcws_bytes, la, st);
+  GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, col0, la, st));
+  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st);
 }
 
 static bool slim_enabled() {
@@ -727,9 +913,26 @@ static bool slim_enabled() {
   return v == 1;
 }
 
+// Number of digit planes of the tcgen05 trailing updates from what the caller knows about the conditioning
+// (cond = max_i A_ii / lambda_min, e.g. (kernel variance + noise) / noise for GPR).  The digit truncation perturbs the
+// trailing matrix by ~1e-11 max_i A_ii with S = 7 and static scales (scripts/static_scale_study.py), i.e. pivots by
+// ~1e-11 cond relative: S = 7 keeps that below 1e-7 up to cond 1e4, S = 8 (2^7 finer) up to ~1e6.5, beyond that the
+// updates run on fp64 DMMA (return 0).  Unknown conditioning (a bare gpk_potrf) takes S = 8.  GPK_TC_SLICES pins S.
+static int g_last_slices = 0;  // diagnostic: digit planes of the most recent fp64 factorisation (0 = DMMA / none)
+int potrf_last_slices() { return g_last_slices; }
+
+static int pick_slices(double cond_hint) {
+  const int pinned = tc_slices();
+  if (pinned) return pinned;
+  if (!(cond_hint > 0.0)) return 8;
+  if (cond_hint <= 1.0e4) return 7;
+  if (cond_hint <= 3.0e6) return 8;
+  return 0;
+}
+
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
-            cudaStream_t st, bool need_dinv) {
+            cudaStream_t st, bool need_dinv, double cond_hint) {
   if (n <= 0) return 0;
   GPK_TRY(leaf_attr<T>());
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
@@ -738,7 +941,16 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(dinv) + (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(T));
   if (n > NB) GPK_TRY(lookahead_init(la, flag, st));
   la.slim = sizeof(T) == 8 && n > NB && slim_enabled();
-  GPK_TRY(potrf_rec<T>(A, n, rows, lda, info, dinv, 0, tcws, tcws_bytes, la, st));
+  la.fuse = la.slim && la.enabled && fuse_enabled();
+  // digit-plane store for the tcgen05 trailing updates: fp64, slim panels (they emit the planes), n >= 2 tc_min_k
+  const int S = pick_slices(cond_hint);
+  if (sizeof(T) == 8) g_last_slices = 0;
+  if (S && la.slim && tcws && tc_enabled() && split_point(n) >= tc_min_k() && tcws_bytes >= tc_planes_bytes(n, rows)) {
+    la.pl = tc_planes_layout(tcws, n, rows, S);
+    g_last_slices = S;
+    if (la.pl.is_static) GPK_TRY(tc_row_exponents((const double*)A, lda, la.pl, st));  // from the ORIGINAL diagonal
+  }
+  GPK_TRY(potrf_rec<T>(A, n, rows, lda, info, dinv, 0, la, st));
   // slim leaves left only the 64x64 diagonal inverses: the full 128x128 block inverses that gpk_trsm consumes are
   // computed now, all blocks in parallel, off the factorisation's critical path (skipped when nobody will use them)
   if (la.slim && need_dinv) GPK_TRY(trtri_diag_t<T>(A, n, lda, dinv, st));
@@ -792,8 +1004,9 @@ int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cuda
   return 0;
 }
 
-template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, void*, size_t, cudaStream_t, bool);
-template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, void*, size_t, cudaStream_t, bool);
+template int potrf_t<float>(float*, int64_t, int64_t, int64_t, int32_t*, float*, void*, size_t, cudaStream_t, bool, double);
+template int potrf_t<double>(double*, int64_t, int64_t, int64_t, int32_t*, double*, void*, size_t, cudaStream_t, bool,
+                             double);
 template int trtri_diag_t<float>(const float*, int64_t, int64_t, float*, cudaStream_t);
 template int trtri_diag_t<double>(const double*, int64_t, int64_t, double*, cudaStream_t);
 template int trsm_t<float>(int, const float*, int64_t, int64_t, float*, int64_t, int64_t, const float*, cudaStream_t);

@@ -4,6 +4,8 @@ from __future__ import annotations
 import ctypes
 from typing import Any, Optional
 
+import numpy as np
+
 from .. import _lib, ops, posteriors
 from ..kernels import Kernel, compile_kernel
 from ..likelihoods import Gaussian
@@ -47,13 +49,65 @@ class GPR(GPModel, InternalDataTrainingLossMixin):
         need = lib.gpk_gpr_lml_ws(N, P, dc)
         if self._ws is None or self._ws.numel() < need:
             self._ws = ops.scratch_bytes(need)
-            self._out = ops.torch().empty((4,), dtype=ops.torch().float64, device=X.device)
+        # a fresh result vector per call: earlier results stay valid when the model is evaluated again
+        self._out = ops.torch().empty((4,), dtype=ops.torch().float64, device=X.device)
         nodes, n_nodes, dims, ard = compile_kernel(self.kernel, D)
         Yc = self._centred_targets()
         _lib.check(lib.gpk_gpr_lml(nodes, n_nodes, dims, ard, ops._p(X), N, ops._ld(X), D, ops._p(Yc), P,
                                    self.likelihood._variance_value(), None, dc, ops._p(self._out), ops._p(self._ws),
                                    ops._stream()), "gpk_gpr_lml")
-        return self._out[0]
+        return ops.objective(self._out, 0, 3)
+
+    def log_marginal_likelihood_and_grad(self):
+        """Value and gradient in ONE fused call (gpk_gpr_lml_grad): the backward pass the reference gets from TensorFlow
+        autodiff through gpr.py:91-107.  Returns (lml, grads): `lml` as log_marginal_likelihood(); `grads` a dict
+        {Parameter: dLML/d(constrained value)} for the kernel variance, the lengthscale(s) and the likelihood variance
+        (NumPy, after one small device->host read).  Covers a single stationary leaf kernel in float64."""
+        from ..kernels.stationaries import Stationary
+
+        k = self.kernel
+        if not isinstance(k, Stationary) or k._op not in (_lib.K_RBF, _lib.K_MATERN12, _lib.K_MATERN32,
+                                                          _lib.K_MATERN52, _lib.K_EXPONENTIAL):
+            raise NotImplementedError("the device backward pass covers a single SquaredExponential / Matern12 / "
+                                      "Matern32 / Matern52 / Exponential kernel")
+        if self.likelihood.variance is None:
+            raise NotImplementedError("the device backward pass covers Gaussian(variance=...)")
+        lib = _lib.load()
+        X, Y = self.data
+        N, D = X.shape
+        P = Y.shape[1]
+        dc = ops.dtype_code(X)
+        if dc != _lib.GPK_F64:
+            raise NotImplementedError("the device backward pass computes in float64")
+        need = lib.gpk_gpr_lml_grad_ws(N, P, dc)
+        if getattr(self, "_gws", None) is None or self._gws.numel() < need:
+            self._gws = ops.scratch_bytes(need)
+        nl = int(k.lengthscales.numpy().size) if k.ard else 1
+        out = ops.torch().empty((6 + nl,), dtype=ops.torch().float64, device=X.device)
+        nodes, n_nodes, dims, ard = compile_kernel(k, D)
+        Yc = self._centred_targets()
+        _lib.check(lib.gpk_gpr_lml_grad(nodes, n_nodes, dims, ard, ops._p(X), N, ops._ld(X), D, ops._p(Yc), P,
+                                        self.likelihood._variance_value(), dc, ops._p(out), 6 + nl, ops._p(self._gws),
+                                        ops._stream()), "gpk_gpr_lml_grad")
+        self._out = out
+        h = out.cpu().numpy()
+        if int(h[3]) != 0:
+            raise ops.NonPositiveDefiniteError(f"Cholesky decomposition was not successful (pivot {int(h[3])} <= 0)")
+        grads = {k.variance: np.asarray(h[4]), self.likelihood.variance: np.asarray(h[5]),
+                 k.lengthscales: (h[6:6 + nl].copy() if k.ard else np.asarray(h[6]))}
+        return ops.objective(out, 0, 3), grads
+
+    def training_loss_and_gradients(self):
+        """(loss, gradients) for the optimiser contract of gpflow/optimizers/scipy.py:322-331: loss = -LML (float) and one
+        gradient per TRAINABLE parameter w.r.t. its UNCONSTRAINED variable, in `trainable_parameters` order."""
+        lml, grads = self.log_marginal_likelihood_and_grad()
+        out = []
+        for p in self.trainable_parameters:
+            if p not in grads:
+                raise NotImplementedError("a trainable parameter has no device gradient (mean-function parameters, "
+                                          "priors and data gradients are outside the hot path)")
+            out.append(-p.unconstrained_gradient(grads[p]))
+        return -float(lml), out
 
     def cholesky_info(self) -> int:
         """0, or the 1-based index of the first non-positive pivot of the last evaluation."""

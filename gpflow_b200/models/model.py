@@ -72,6 +72,31 @@ class GPModel(BayesianModel):
         return self.likelihood.predict_log_density(X, f_mean, f_var, Y)
 
 
+class LossClosure:
+    """What `training_loss_closure()` returns: calling it evaluates the loss (as in the reference); models with a device
+    backward pass also give the optimiser `value_and_gradients(variables)` -> (loss, [d loss / d unconstrained variable])
+    in the order of `variables` (the pair gpflow/optimizers/scipy.py:300-316 obtains from a GradientTape)."""
+
+    def __init__(self, model, loss_fn: Callable[[], Any]):
+        self._model, self._loss_fn = model, loss_fn
+        if hasattr(model, "training_loss_and_gradients"):
+            self.value_and_gradients = self._value_and_gradients
+
+    def __call__(self):
+        return self._loss_fn()
+
+    def _value_and_gradients(self, variables=None):
+        loss, grads = self._model.training_loss_and_gradients()
+        params = self._model.trainable_parameters
+        if variables is None:
+            return loss, grads
+        by_id = {id(p): g for p, g in zip(params, grads)}
+        missing = [v for v in variables if id(v) not in by_id]
+        if missing:
+            raise ValueError("a variable passed to the optimiser is not a trainable parameter of the model")
+        return loss, [by_id[id(v)] for v in variables]
+
+
 class InternalDataTrainingLossMixin:
     """training_mixins.py:43-78."""
 
@@ -79,7 +104,7 @@ class InternalDataTrainingLossMixin:
         return self._training_loss()
 
     def training_loss_closure(self, *, compile: bool = True) -> Callable[[], Any]:
-        return self.training_loss
+        return LossClosure(self, self.training_loss)
 
 
 class ExternalDataTrainingLossMixin:

@@ -10,10 +10,7 @@ from ..likelihoods import Gaussian
 from ..mean_functions import MeanFunction, Zero
 from .model import GPModel, InternalDataTrainingLossMixin, data_input_to_tensor
 
-_WS_CACHE = {}
-
-
-def _sgpr_fused(X, Y, kernel, inducing_variable, likelihood, mean_function, cache=None, jitter=None):
+def _sgpr_fused(X, Y, kernel, inducing_variable, likelihood, mean_function, cache=None, jitter=None, owner=None):
     """One gpk_sgpr_elbo call; returns the device fp64 vector
     [elbo, const, logdet, quad, trace_k, trace_q, half_logdet_b, info]."""
     lib = _lib.load()
@@ -23,11 +20,13 @@ def _sgpr_fused(X, Y, kernel, inducing_variable, likelihood, mean_function, cach
     M = Z.shape[0]
     dc = ops.dtype_code(X)
     need = lib.gpk_sgpr_elbo_ws(N, M, P, dc)
-    key = (str(X.device), need)
-    ws = _WS_CACHE.get(key)
-    if ws is None:
-        _WS_CACHE.clear()
-        ws = _WS_CACHE[key] = ops.scratch_bytes(need)
+    # the scratch workspace belongs to the calling model / posterior instance (`owner`): evaluations of different
+    # instances on different streams never share it
+    ws = getattr(owner, "_sgpr_ws", None) if owner is not None else None
+    if ws is None or ws.numel() < need or ws.device != X.device:
+        ws = ops.scratch_bytes(need)
+        if owner is not None:
+            owner._sgpr_ws = ws
     out = ops.torch().empty((8,), dtype=ops.torch().float64, device=X.device)
     if mean_function is None or isinstance(mean_function, Zero):
         Yc = Y
@@ -74,8 +73,9 @@ class SGPR(GPModel, InternalDataTrainingLossMixin):
     def elbo(self):
         """sgpr.py:276-289 in one fused call; device fp64 scalar."""
         X, Y = self.data
-        self._last = _sgpr_fused(X, Y, self.kernel, self.inducing_variable, self.likelihood, self.mean_function)
-        return self._last[0]
+        self._last = _sgpr_fused(X, Y, self.kernel, self.inducing_variable, self.likelihood, self.mean_function,
+                                 owner=self)
+        return ops.objective(self._last, 0, 7)
 
     def elbo_terms(self):
         """(const, logdet_term, quad_term) of the last evaluation as device scalars (sgpr.py:214-271)."""

@@ -55,11 +55,26 @@ class SVGP(GPModel, ExternalDataTrainingLossMixin):
     def maximum_log_likelihood_objective(self, data):  # svgp.py:159-160
         return self.elbo(data)
 
-    def elbo(self, data, *, latent_range: Optional[Tuple[int, int]] = None):
+    def elbo(self, data, *, latent_range: Optional[Tuple[int, int]] = None, batch_total: Optional[int] = None,
+             include_kl: bool = True):
         """svgp.py:166-181 in ONE fused call (gpk_svgp_elbo) for a single-output kernel and Gaussian
-        likelihood.  `latent_range=(p0, p1)` evaluates the share of latent GPs [p0, p1) (data term and
-        KL of those latents) for latent sharding across GPUs; the shares sum to the full ELBO.
-        Returns a device fp64 scalar."""
+        likelihood.  Returns a device fp64 scalar.  Sharding over GPUs (see sharding.py):
+        `latent_range=(p0, p1)` evaluates the share of latent GPs [p0, p1) (data term and KL of those latents);
+        `batch_total=B` says that `data` holds only some ROWS of a minibatch of B rows (the data term is a sum over
+        rows rescaled by num_data / B, svgp.py:173-181) and `include_kl=False` leaves the KL to another rank;
+        in both cases the shares of all ranks sum to the full ELBO."""
+        out = self._fused(data, latent_range, 0, None, batch_total)
+        if include_kl:
+            return ops.objective(out, 0, 3)
+        share = ops.copy(out[1:2])                     # sum of variational expectations (unscaled)
+        ops.axpby(0.0, share, self._scale(data, batch_total), share)
+        return share[0]
+
+    def _scale(self, data, batch_total):
+        B = int(data[0].shape[0]) if batch_total is None else int(batch_total)
+        return 1.0 if self.num_data is None else float(self.num_data) / B     # svgp.py:175-180
+
+    def _fused(self, data, latent_range, stage, cols, batch_total=None):
         if isinstance(self.kernel, MultioutputKernel) or not isinstance(self.likelihood, Gaussian):
             raise NotImplementedError("fused SVGP.elbo covers single-output kernels with a Gaussian likelihood")
         lib = _lib.load()
@@ -77,15 +92,37 @@ class SVGP(GPModel, ExternalDataTrainingLossMixin):
         out = ops.torch().empty((4,), dtype=ops.torch().float64, device=X.device)
         Yc = Y if isinstance(self.mean_function, Zero) else ops.axpby(-1.0, self.mean_function(X), 1.0, ops.copy(Y))
         q_mu, q_sqrt = ops.to_device(self.q_mu), ops.to_device(self.q_sqrt)
-        scale = 1.0 if self.num_data is None else float(self.num_data) / B     # svgp.py:175-180
+        scale = self._scale(data, batch_total)
         p0, p1 = (0, P) if latent_range is None else latent_range
+        c0, c1 = (0, B) if cols is None else cols
         nodes, n_nodes, dims, ard = compile_kernel(self.kernel, D)
-        _lib.check(lib.gpk_svgp_elbo(nodes, n_nodes, dims, ard, ops._p(X), B, ops._ld(X), D, ops._p(Yc), P, ops._p(Z),
-                                     M, ops._ld(Z), ops._p(q_mu), ops._p(q_sqrt), int(self.q_diag), int(self.whiten),
-                                     self.likelihood._variance_value(), scale, config.default_jitter(), p0, p1, dc,
-                                     ops._p(out), ops._p(self._ws), ops._stream()), "gpk_svgp_elbo")
+        _lib.check(lib.gpk_svgp_elbo_staged(nodes, n_nodes, dims, ard, ops._p(X), B, ops._ld(X), D, ops._p(Yc), P,
+                                            ops._p(Z), M, ops._ld(Z), ops._p(q_mu), ops._p(q_sqrt), int(self.q_diag),
+                                            int(self.whiten), self.likelihood._variance_value(), scale,
+                                            config.default_jitter(), p0, p1, stage, c0, c1, dc, ops._p(out),
+                                            ops._p(self._ws), ops._stream()), "gpk_svgp_elbo")
         self._last = out
-        return out[0]
+        return out
+
+    def solve_columns(self, data, cols: Tuple[int, int]):
+        """Stage 1 of the column-sharded evaluation: Kuu, chol(Kuu) and A[:, c0:c1] = Lm^-1 Kuf[:, c0:c1] for this rank's
+        minibatch columns (conditionals/util.py:125).  Returns the workspace matrix A [M, B] (a strided view; only the
+        columns [c0, c1) are valid) for the all-gather of sharding.svgp_elbo_latent_sharded."""
+        self._fused(data, None, 1, cols)
+        lib = _lib.load()
+        X = data[0]
+        B, M, P = int(X.shape[0]), int(self.inducing_variable.num_inducing), self.num_latent_gps
+        import ctypes
+        ld = ctypes.c_int64(0)
+        dt = ops.torch_dtype()
+        off = lib.gpk_svgp_elbo_A(B, M, P, ops.dtype_code(ops.to_device(X)), ctypes.byref(ld))
+        es = 8 if dt == ops.torch().float64 else 4
+        flat = self._ws[off:off + M * ld.value * es].view(dt)
+        return flat.view(M, ld.value)[:, :B]
+
+    def elbo_from_columns(self, data, latent_range: Tuple[int, int]):
+        """Stage 2: the share of latents [p0, p1) with A complete in the workspace (after the all-gather)."""
+        return self._fused(data, latent_range, 2, None)[0]
 
     def elbo_unfused(self, data):
         """svgp.py:166-181 composed from the public operators (prior_kl, predict_f,

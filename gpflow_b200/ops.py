@@ -120,6 +120,51 @@ class NonPositiveDefiniteError(_lib.GpkError):
     """Analogue of TF's InvalidArgumentError 'Cholesky decomposition was not successful'."""
 
 
+_OBJECTIVE_CLS = None
+
+
+def objective(out, value_idx: int = 0, info_idx: Optional[int] = None):
+    """Scalar result of a fused objective: the 0-d DEVICE tensor out[value_idx] (no synchronisation), typed so that
+    reading it on the host -- float(v), v.item(), v.cpu() -- also reads out[info_idx] in the same transfer and raises
+    NonPositiveDefiniteError when the factorisation inside the evaluation met a non-positive pivot, as
+    tf.linalg.cholesky raises InvalidArgumentError in the reference (gpflow/models/gpr.py:102).  `v.unchecked()`
+    returns the plain tensor."""
+    global _OBJECTIVE_CLS
+    T = torch()
+    if _OBJECTIVE_CLS is None:
+        class Objective(T.Tensor):
+            __torch_function__ = T._C._disabled_torch_function_impl  # ops on it yield plain tensors
+
+            def unchecked(self):
+                return self.as_subclass(T.Tensor)
+
+            def _host_value(self):
+                src = getattr(self, "_gpk_out", None)
+                if src is None:
+                    return T.Tensor.item(self.as_subclass(T.Tensor))
+                out_, vi, ii = src
+                h = out_.cpu()
+                if ii is not None and int(h[ii]) != 0:
+                    raise NonPositiveDefiniteError(
+                        f"Cholesky decomposition was not successful (pivot {int(h[ii])} <= 0)")
+                return float(h[vi])
+
+            def item(self):
+                return self._host_value()
+
+            def __float__(self):
+                return float(self._host_value())
+
+            def cpu(self, *a, **k):
+                self._host_value()
+                return self.as_subclass(T.Tensor).cpu(*a, **k)
+
+        _OBJECTIVE_CLS = Objective
+    v = out[value_idx].as_subclass(_OBJECTIVE_CLS)
+    v._gpk_out = (out, value_idx, info_idx)
+    return v
+
+
 def potrf(A, n: Optional[int] = None, *, check_info: bool = True):
     """In-place lower Cholesky of the leading n x n block of A [rows, >=n]; returns (A, dinv)."""
     rows = A.shape[0]
@@ -166,7 +211,8 @@ def gemm(A, B, *, transa: bool = False, transb: bool = False, alpha: float = 1.0
     if k != kb:
         raise ValueError(f"gemm: inner dimensions differ ({k} vs {kb})")
     if out is None:
-        out = empty((n,) if flags & _lib.GPK_GEMM_COLSUMSQ else (m, n), like=A)
+        # the column-sum-of-squares epilogue ACCUMULATES (atomicAdd) into its output: start from zero
+        out = full((n,), 0.0, like=A) if flags & _lib.GPK_GEMM_COLSUMSQ else empty((m, n), like=A)
     ldc = 0 if flags & _lib.GPK_GEMM_COLSUMSQ else _ld(out)
     check(_lib.load().gpk_gemm(int(transa), int(transb), m, n, k, float(alpha), _p(A), _ld(A), _p(B), _ld(B),
                                float(beta), _p(out), ldc, dtype_code(A), flags, _stream()), "gpk_gemm")
@@ -210,7 +256,15 @@ def tril_sumsq(A, *, scale: float = 1.0, out=None, accumulate: bool = False):
 
 # ---- elementwise -------------------------------------------------------------------------------------
 def axpby(a: float, X, b: float, Y):
-    """Y = a X + b Y (2-D or 1-D)."""
+    """Y = a X + b Y (2-D or 1-D).  X [N, 1] against Y [N, P] broadcasts along the columns (the reference's
+    `Y - mean_function(X)` with a single-column mean, gpflow/models/gpr.py:98); any other shape mismatch raises."""
+    if tuple(X.shape) != tuple(Y.shape):
+        if X.dim() == 2 and Y.dim() == 2 and X.shape[0] == Y.shape[0] and X.shape[1] == 1:
+            for p in range(Y.shape[1]):
+                axpby(a, X, b, Y[:, p:p + 1])
+            return Y
+        if X.numel() != Y.numel() or (X.dim() > 1 and Y.dim() > 1):
+            raise ValueError(f"axpby: shapes {tuple(X.shape)} and {tuple(Y.shape)} do not match")
     if X.dim() <= 1:
         m, n, ldx, ldy = 1, X.numel(), X.numel(), Y.numel()
     else:

@@ -155,7 +155,7 @@ class SGPRPosterior(AbstractPosterior):
         LB = ops.empty((M, M), like=self.X_data)
         c = ops.empty((M, P), like=self.X_data)
         _sgpr_fused(self.X_data, self.Y_data, self.kernel, self.inducing_variable, self.likelihood,
-                    self.mean_function, cache=(L, LB, c))
+                    self.mean_function, cache=(L, LB, c), owner=self)
         return L, LB, c
 
     def _conditional_with_precompute(self, cache, Xnew, full_cov: bool = False, full_output_cov: bool = False):

@@ -194,6 +194,20 @@ GPK_API int gpk_gpr_lml(const gpk_knode* nodes, int n_nodes, const int32_t* dims
                 double noise_variance, const void* noise_vec, int dtype, double* out, void* ws,
                 void* stream);
 
+/* GPR log marginal likelihood AND its gradient w.r.t. the kernel variance, the likelihood variance and the
+ * lengthscale(s): the backward pass that TensorFlow autodiff supplies to the reference's optimiser
+ * (gpflow/optimizers/scipy.py:78-228 -> models/training_mixins.py:43-78 -> models/gpr.py:91-107), written out as
+ * dLML/dK = 1/2 (alpha alpha^T - P K^-1), K^-1 = L^-T L^-1 from the factor of the forward pass, and one K-build-shaped
+ * reduction sum_ij (dLML/dK)_ij dK_ij/dtheta.  Covers a single stationary leaf kernel (RBF, Matern12/32/52,
+ * Exponential; scalar or ARD lengthscale), float64.
+ *   out: device double[n_out]: [0..3] as gpk_gpr_lml, [4] d/dvariance, [5] d/dnoise_variance,
+ *        [6 .. 6 + n_l) d/dlengthscale (n_l = 1, or the number of ARD lengthscales); n_out >= 6 + n_l.
+ *   ws:  gpk_gpr_lml_grad_ws(N, P, dtype) bytes. */
+GPK_API size_t gpk_gpr_lml_grad_ws(int64_t N, int64_t P, int dtype);
+GPK_API int gpk_gpr_lml_grad(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard,
+                     const void* X, int64_t N, int64_t ldx, int64_t D, const void* Yc, int64_t P,
+                     double noise_variance, int dtype, double* out, int n_out, void* ws, void* stream);
+
 /* SGPR.elbo (gpflow/models/sgpr.py:181-289).  Yc = Y - m(X) [N,P] contiguous, Z [M,D].
  * out: device double[8] = {elbo, const, logdet, quad, trace_k, trace_q, half_logdet_b, info}.
  * If `cache_L`, `cache_LB`, `cache_c` are non-NULL they receive L [M,M], LB [M,M], c [M,P]
@@ -219,21 +233,46 @@ GPK_API int gpk_svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* di
                   double jitter, int p_begin, int p_end, int dtype, double* out, void* ws,
                   void* stream);
 
+/* The same evaluation in two stages, for latent-GP sharding over GPUs with a COLUMN-SHARDED triangular solve
+ * (derived from conditionals/util.py:125-164: every column of A = Lm^-1 Kuf depends on its own x_n only):
+ *   stage 1: Kuu, chol(Kuu), Kuf[:, col_begin:col_end] and A[:, col_begin:col_end] = Lm^-1 Kuf[:, ...], left in place in
+ *            the workspace matrix A [M, ld] (gpk_svgp_elbo_A returns its byte offset in `ws` and `ld`); the caller
+ *            all-gathers the column blocks of A between the ranks (NCCL);
+ *   stage 2: everything after the solve (fmean, fvar, variational expectations, KL) for the latents [p_begin, p_end)
+ *            with A complete in the workspace.  stage 0 = gpk_svgp_elbo.  whiten = 1 only. */
+GPK_API size_t gpk_svgp_elbo_A(int64_t B, int64_t M, int64_t P, int dtype, int64_t* ld);
+GPK_API int gpk_svgp_elbo_staged(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const double* ard,
+                         const void* Xb, int64_t B, int64_t ldx, int64_t D, const void* Yc, int64_t P,
+                         const void* Z, int64_t M, int64_t ldz, const void* q_mu, const void* q_sqrt,
+                         int q_diag, int whiten, double noise_variance, double num_data_scale, double jitter,
+                         int p_begin, int p_end, int stage, int64_t col_begin, int64_t col_end, int dtype,
+                         double* out, void* ws, void* stream);
+
 /* ---- Instrumentation (bench.py / tests; not on the numeric path) ---------------------------- */
 /* Number of CUDA kernels launched by this library since the last reset. */
 GPK_API int64_t gpk_launch_count(void);
 GPK_API void gpk_launch_count_reset(void);
 /* Per-kernel-class device timing with CUDA events recorded on the launch stream around every
- * launch (single-threaded diagnostic).  Classes: 0 kbuild, 1 tiled GEMM (trailing update / TRSM
- * blocks / SYRK), 2 potrf leaf (128x128 factor+invert), 3 skinny GEMM, 4 reductions/elementwise.
+ * launch (single-threaded diagnostic).  Classes: 0 kbuild, 1 tiled DMMA / SIMT GEMM (small-K trailing
+ * updates, TRSM blocks), 2 potrf leaf (128x128 factor+invert; includes its look-ahead spin), 3 skinny
+ * GEMM, 4 reductions/elementwise/slicing, 5 tcgen05 kernels (int8 digit SYRK, tf32 GEMM), 6 panel solve.
  * gpk_prof_read synchronises, writes summed milliseconds and launch counts for `n` classes and
- * clears the records. */
-#define GPK_PROF_CLASSES 5
+ * clears the records; gpk_prof_read2 also returns the operations ISSUED per class (class 5: MACs on
+ * the tensor pipe, padding tiles included). */
+#define GPK_PROF_CLASSES 8
 /* Tuning aid: runs ONE fp64 128x128 leaf (factor+invert) and stores clock64() at its phase
  * boundaries into dbg[0..9] (device int64). */
 GPK_API int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* stream);
 GPK_API int gpk_prof_enable(int on);
 GPK_API int gpk_prof_read(double* ms, int64_t* launches, int n);
+GPK_API int gpk_prof_read2(double* ms, int64_t* launches, double* work, int n);
+/* Pipe peaks measured in place (operands resident, every SM busy): out_host[0] = tcgen05 kind::i8 issue peak in
+ * T(int8 op)/s (2 per MAC), out_host[1] = mma.sync.m8n8k4.f64 peak in TFLOP/s, out_host[2] = SM count.  Synchronises.
+ * The roofline denominators bench.py reports for syrk_i8_kernel and the DMMA kernels. */
+GPK_API int gpk_peak_probe(double* out_host, void* stream);
+/* Digit planes S used by the tcgen05 trailing updates of the most recent fp64 factorisation on this process (chosen from
+ * the conditioning hint of the caller: 7, 8, or 0 = the updates ran on fp64 DMMA). */
+GPK_API int gpk_potrf_last_slices(void);
 
 #ifdef __cplusplus
 }

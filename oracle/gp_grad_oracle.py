@@ -11,7 +11,7 @@ likelihood variance.  It is pinned by central finite differences of gp_oracle.gp
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Tuple, Union
 
 import numpy as np
 
@@ -19,25 +19,34 @@ from . import gp_oracle as O
 
 
 def stationary_dK(kernel: O.Stationary, X: np.ndarray) -> Dict[str, np.ndarray]:
-    """dK/d(variance) and dK/d(lengthscales) (scalar lengthscale) of an isotropic stationary kernel on X.
-    With r = d / l:  dk/dl = k'(r) (-r / l).  (stationaries.py:209-210, 270-271, 290-292, 311-313)"""
+    """dK/d(variance) and dK/d(lengthscales) of a stationary kernel on X; with an ARD lengthscale vector the entry
+    "lengthscales" is a [D_active, N, N] stack.  With s = sum_d ((x_d - x'_d) / l_d)^2 and r = sqrt(s):
+    dk/dl_d = (dk/ds) (-2 (x_d - x'_d)^2 / l_d^3).  (stationaries.py:209-210, 250-251, 270-271, 290-292, 311-313)"""
     var = float(np.asarray(kernel.variance))
-    ell = float(np.asarray(kernel.lengthscales))
+    ell = np.asarray(kernel.lengthscales, dtype=np.float64)
     K = kernel(X)
-    r2 = np.maximum(kernel.scaled_squared_euclid_dist(kernel.slice(X)[0]), 0.0)
+    Xs = kernel.slice(X)[0]
+    r2 = np.maximum(kernel.scaled_squared_euclid_dist(Xs), 0.0)
     r = np.sqrt(r2)
-    if isinstance(kernel, O.SquaredExponential):
-        dl = K * r2 / ell
-    elif isinstance(kernel, O.Matern12):
-        dl = K * r / ell
-    elif isinstance(kernel, O.Matern32):
-        s3 = np.sqrt(3.0)
-        dl = 3.0 * var * r2 * np.exp(-s3 * r) / ell
-    elif isinstance(kernel, O.Matern52):
-        s5 = np.sqrt(5.0)
-        dl = (5.0 / 3.0) * var * r2 * (1.0 + s5 * r) * np.exp(-s5 * r) / ell
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if isinstance(kernel, O.SquaredExponential):
+            dkds = -0.5 * K
+        elif isinstance(kernel, O.Exponential):
+            dkds = np.where(r > 0, -K / (4.0 * r), 0.0)
+        elif isinstance(kernel, O.Matern12):
+            dkds = np.where(r > 0, -K / (2.0 * r), 0.0)
+        elif isinstance(kernel, O.Matern32):
+            dkds = -1.5 * var * np.exp(-np.sqrt(3.0) * r)
+        elif isinstance(kernel, O.Matern52):
+            s5 = np.sqrt(5.0)
+            dkds = -(5.0 / 6.0) * var * (1.0 + s5 * r) * np.exp(-s5 * r)
+        else:
+            raise NotImplementedError(type(kernel).__name__)
+    if ell.ndim == 0:
+        dl = dkds * (-2.0 * r2 / float(ell))
     else:
-        raise NotImplementedError(type(kernel).__name__)
+        diff2 = (Xs[:, None, :] - Xs[None, :, :]) ** 2            # [N, N, D]
+        dl = np.stack([dkds * (-2.0 * diff2[:, :, d] / ell[d] ** 3) for d in range(ell.shape[0])])
     return {"variance": K / var, "lengthscales": dl}
 
 
@@ -54,6 +63,8 @@ def gpr_lml_and_grad(X: np.ndarray, Y: np.ndarray, kernel: O.Stationary, noise_v
     Kinv = Linv.T @ Linv
     G = 0.5 * (alpha @ alpha.T - P * Kinv)                               # dLML/dK
     dK = stationary_dK(kernel, X)
-    grad = {name: float(np.sum(G * d)) for name, d in dK.items()}
+    grad = {"variance": float(np.sum(G * dK["variance"]))}
+    dl = dK["lengthscales"]
+    grad["lengthscales"] = float(np.sum(G * dl)) if dl.ndim == 2 else np.array([np.sum(G * d) for d in dl])
     grad["noise_variance"] = float(np.trace(G))
     return lml, grad

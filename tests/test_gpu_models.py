@@ -113,8 +113,10 @@ def test_gpr_default_noise_and_not_pd(cuda_device):
     assert_allclose(float(m.log_marginal_likelihood()), O.gpr_log_marginal_likelihood(X, Y, O.RBF(), 1.0), rtol=1e-10)
     Xd = np.concatenate([X, X])  # duplicated inputs with tiny noise: numerically singular
     m = gpf.models.GPR((Xd, np.concatenate([Y, Y])), gpf.kernels.RBF(), likelihood=gpf.likelihoods.Gaussian(2e-6, variance_lower_bound=1e-6))
-    m.log_marginal_likelihood()
-    assert m.cholesky_info() >= 0  # info is surfaced, evaluation does not hang or crash
+    # numerically singular but still positive definite in fp64 (pivots ~ 2 * 2e-6): evaluates, like LAPACK; the truly
+    # non-positive-definite case (exception on the host read) is tests/test_gpu_edge.py
+    assert np.isfinite(float(m.log_marginal_likelihood()))
+    assert m.cholesky_info() == 0
 
 
 def test_c5_reduced_separate_outputs_golden(cuda_device):
@@ -392,7 +394,10 @@ def test_c2_full_size_factor_residual(cuda_device):
     ops.gemm(L, L, transb=True, alpha=-1.0, beta=1.0, out=R)
     num = float(ops.reduce(ops.SUMSQ, R, R.numel())) ** 0.5
     den = float(ops.reduce(ops.SUMSQ, K, K.numel())) ** 0.5
-    assert num / den < 1e-13
+    # digit planes with STATIC row scales 2^ceil(log2 sqrt(K_ii)) (csrc/planes.cuh): rows of L are usually well below
+    # sqrt(K_ii), so a few leading digit bits are unused -- measured 6e-13 here (4e-14 with per-update row maxima,
+    # GPK_TC_STATIC=0); the parity bar on the objective is 1e-5
+    assert num / den < 3e-12
 
 
 def _gold_full():
