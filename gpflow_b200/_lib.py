@@ -33,6 +33,20 @@ class KNode(ctypes.Structure):
     ]
 
 
+KAUX_COSINE, KAUX_PERIODIC, KAUX_ARCCOS, KAUX_COREGION = range(4)
+GPK_KAUX_MAXD = 32
+
+
+class KAux(ctypes.Structure):
+    """Mirror of `gpk_kaux` (include/gpk.h): kernels that are not functions of a Gram term."""
+
+    _fields_ = [
+        ("op", c_int32), ("base", c_int32), ("order", c_int32), ("n_dims", c_int32), ("table_dim", c_int32),
+        ("pad_", c_int32), ("variance", c_double), ("alpha", c_double), ("bias", c_double), ("table", c_void_p),
+        ("dims", c_int32 * GPK_KAUX_MAXD), ("scale", c_double * GPK_KAUX_MAXD), ("period", c_double * GPK_KAUX_MAXD),
+    ]
+
+
 _KN = POINTER(KNode)
 _I32 = POINTER(c_int32)
 _F64 = POINTER(c_double)
@@ -68,6 +82,13 @@ SIGNATURES = {
                                         c_void_p, c_int, c_void_p]),
     "gpk_gaussian_log_density": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_int,
                                          c_void_p]),
+    "gpk_kaux": (c_int, [POINTER(KAux), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int,
+                         c_void_p]),
+    "gpk_kaux_diag": (c_int, [POINTER(KAux), c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "gpk_changepoint_weights": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_double, c_double, c_int, c_double,
+                                        c_double, c_void_p, c_int, c_void_p]),
+    "gpk_clamp_min": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_double, c_int, c_int, c_void_p]),
+    "gpk_hadamard": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "gpk_launch_count": (c_int64, []),
     "gpk_launch_count_reset": (None, []),
     "gpk_debug_leaf": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -75,3 +75,39 @@ def conditional(Xnew, inducing_variable, kernel: Kernel, f, *, full_cov: bool = 
     posterior = create_posterior(kernel, iv, f, q_sqrt, whiten=white, mean_function=None,
                                  precompute_cache=PrecomputeCacheType.NOCACHE)
     return posterior.fused_predict_f(Xnew, full_cov=full_cov, full_output_cov=full_output_cov)
+
+
+def sample_mvn(mean, cov, full_cov: bool, num_samples: Optional[int] = None, *, eps=None, generator=None):
+    """conditionals/util.py:179-211 for 2-D `mean` [N, D]: a sample (or `num_samples` samples, leading axis) from
+    N(mean, cov) with cov [N, D] (full_cov=False: independent entries) or [N, D, D] (full_cov=True: one D x D covariance per
+    row, factorised with the default jitter).  The standard-normal draws come from `eps` when given ([S, N, D] / [N, D, S], the
+    reference's shapes) -- that is how the parity tests feed the oracle the same noise -- else from torch.randn (input
+    generation; all arithmetic on the draws is libgpk)."""
+    T = ops.torch()
+    mean, cov = ops.to_device(mean), ops.to_device(cov)
+    S = 1 if num_samples is None else int(num_samples)
+    N, D = mean.shape
+    if not full_cov:
+        e = T.randn((S, N, D), dtype=mean.dtype, device=mean.device, generator=generator) if eps is None else ops.to_device(eps)
+        sd = ops.copy(cov)
+        _lib.check(_lib.load().gpk_clamp_min(ops._p(sd), N, D, ops._ld(sd), 0.0, 2, ops.dtype_code(sd), ops._stream()),
+                   "gpk_clamp_min")
+        out = ops.copy(e.reshape(S * N, D)).view(S, N, D)
+        for s_ in range(S):
+            ops.hadamard_(out[s_], sd)
+            ops.axpby(1.0, mean, 1.0, out[s_])
+    else:
+        e = T.randn((N, D, S), dtype=mean.dtype, device=mean.device, generator=generator) if eps is None else ops.to_device(eps)
+        tmp = ops.empty((N, S, D), like=mean)                                  # per row n: (chol_n eps_n)^T [S, D]
+        for n in range(N):
+            C = ops.copy(cov[n])
+            ops.add_diag_(C, config.default_jitter())                          # util.py:202-204
+            Lc, _ = ops.potrf(C)
+            ops.tril_(Lc)
+            smp = ops.gemm(Lc, e[n])                                           # [D, S]
+            ops.transpose(smp, out=tmp[n])
+        out = ops.empty((S, N, D), like=mean)
+        for s_ in range(S):                                                    # [N, S, D] -> [S, N, D], + mean
+            ops.axpby(1.0, tmp[:, s_, :], 0.0, out[s_])
+            ops.axpby(1.0, mean, 1.0, out[s_])
+    return out[0] if num_samples is None else out

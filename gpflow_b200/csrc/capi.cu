@@ -70,6 +70,13 @@ int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype,
 
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st);
 int peak_probe(double* out_host, cudaStream_t st);
+int kaux_impl(const gpk_kaux_desc* d, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2,
+              void* K, int64_t ldk, int dtype, cudaStream_t st);
+int kaux_diag_impl(const gpk_kaux_desc* d, const void* X, int64_t N, int64_t ldx, void* out, int dtype, cudaStream_t st);
+int cp_weights_impl(const void* X, int64_t N, int64_t ldx, int dim, int has_lo, double loc_lo, double steep_lo,
+                    int has_hi, double loc_hi, double steep_hi, void* out, int dtype, cudaStream_t st);
+int hadamard_impl(int64_t m, int64_t n, const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype, cudaStream_t st);
+int clamp_min_impl(void* A, int64_t m, int64_t n, int64_t lda, double lower, int square, int dtype, cudaStream_t st);
 int potrf_last_slices();
 size_t gpr_lml_ws(int64_t N, int64_t P, int dtype);
 int gpr_lml(const gpk_knode*, int, const int32_t*, const double*, const void*, int64_t, int64_t, int64_t, const void*,
@@ -119,6 +126,30 @@ int gpk_peak_probe(double* out_host, void* stream) {
 int gpk_prof_read(double* ms, int64_t* launches, int n) { return gpk_prof_read2(ms, launches, nullptr, n); }
 
 int gpk_potrf_last_slices(void) { return potrf_last_slices(); }
+
+int gpk_kaux(const gpk_kaux_desc* desc, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2, void* K,
+             int64_t ldk, int dtype, void* stream) {
+  GPK_DTYPE_OK("kaux");
+  return kaux_impl(desc, X, N, ldx, X2, N2, ldx2, K, ldk, dtype, (cudaStream_t)stream);
+}
+int gpk_kaux_diag(const gpk_kaux_desc* desc, const void* X, int64_t N, int64_t ldx, void* out, int dtype, void* stream) {
+  GPK_DTYPE_OK("kaux_diag");
+  return kaux_diag_impl(desc, X, N, ldx, out, dtype, (cudaStream_t)stream);
+}
+int gpk_changepoint_weights(const void* X, int64_t N, int64_t ldx, int dim, int has_lo, double loc_lo, double steep_lo,
+                            int has_hi, double loc_hi, double steep_hi, void* out, int dtype, void* stream) {
+  GPK_DTYPE_OK("changepoint_weights");
+  return cp_weights_impl(X, N, ldx, dim, has_lo, loc_lo, steep_lo, has_hi, loc_hi, steep_hi, out, dtype,
+                         (cudaStream_t)stream);
+}
+int gpk_clamp_min(void* A, int64_t m, int64_t n, int64_t lda, double lower, int square, int dtype, void* stream) {
+  GPK_DTYPE_OK("clamp_min");
+  return clamp_min_impl(A, m, n, lda, lower, square, dtype, (cudaStream_t)stream);
+}
+int gpk_hadamard(int64_t m, int64_t n, const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype, void* stream) {
+  GPK_DTYPE_OK("hadamard");
+  return hadamard_impl(m, n, X, ldx, Y, ldy, dtype, (cudaStream_t)stream);
+}
 
 int gpk_prof_read2(double* ms, int64_t* launches, double* work, int n) {
   GPK_CHECK_ARG(ms && launches && n > 0, "prof_read: bad arguments");

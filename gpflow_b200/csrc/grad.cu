@@ -155,7 +155,9 @@ __global__ void put_dinv_kernel(double* __restrict__ L, int64_t ldl, int64_t n, 
   const double* src = dinv + (size_t)blockIdx.x * NB * NB;
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int r = e / NB, c = e % NB;
-    if (b0 + r < n && c <= r) L[(b0 + r) * ldl + b0 + c] = src[r * NB + c];
+    // the strict upper part of the block is zeroed: lauum reads the block as a dense operand, and the workspace above
+    // the diagonal tiles of the K-build is uninitialised (0 x NaN)
+    if (b0 + r < n && b0 + c < n) L[(b0 + r) * ldl + b0 + c] = c <= r ? src[r * NB + c] : 0.0;
   }
 }
 

@@ -573,32 +573,45 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
       atomicAdd(fu.flag + 2, 1);
     }
   }
-  // ---- digit planes of the finished rows (static scales; the extra rows below the square part are sliced elsewhere)
-  if (em.pl.planes && nb == NB) {
+  // ---- digit planes of the finished rows (static scales; the extra rows below the square part are sliced elsewhere).
+  // One item = 16 consecutive k of one row = 16 contiguous bytes of every plane in the tile image; consecutive lanes
+  // take consecutive rows, so a warp's 16-byte stores fill whole 128-byte lines (4-byte stores per lane cost 8 us per
+  // launch: as much as the slicing pass this replaces).
+  auto emit_planes = [&]() {
+    if (!(em.pl.planes && nb == NB)) return;
+    if (!fu.C) __syncthreads();  // (the fused path has passed a barrier already) all warps' rows are in Bs
     const int S = em.pl.S;
 #pragma unroll 1
-    for (int rr = 0; rr < 8; ++rr) {
-      const int64_t row = r0 + w * 8 + rr, grow = em.row_g0 + row;
-      if (row < rows && grow < em.pl.n_sq) {
-        const double inv = 1.0 / em.pl.rowscale[grow];  // exact: a power of two
-        double v[4];
+    for (int e = tid; e < PR * 8; e += 256) {
+      const int rl = e & (PR - 1), ch = e >> 6;  // local row, 16-column chunk
+      const int64_t row = r0 + rl, grow = em.row_g0 + row;
+      if (row >= rows || grow >= em.pl.n_sq) continue;
+      const double inv = 1.0 / em.pl.rowscale[grow];  // exact: a power of two
+      double v[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = Bw[rr * PLB + lane * 4 + u] * inv;
-        const int64_t kcol = em.col_g0 + lane * 4;
-        int8_t* tb = em.pl.tile(grow >> 7, kcol / TC_KB) + tc_tile_off((int)(grow & 127), (int)(kcol % TC_KB));
-        for (int s2 = 0; s2 < S; ++s2) {
-          uint32_t wd = 0;
+      for (int u = 0; u < 8; ++u) {
+        const double2 t2 = *reinterpret_cast<const double2*>(Bs + rl * PLB + ch * 16 + 2 * u);
+        v[2 * u] = t2.x * inv;
+        v[2 * u + 1] = t2.y * inv;
+      }
+      const int64_t kcol = em.col_g0 + ch * 16;
+      int8_t* tb = em.pl.tile(grow >> 7, kcol / TC_KB) + tc_tile_off((int)(grow & 127), (int)(kcol % TC_KB));
+      for (int s2 = 0; s2 < S; ++s2) {
+        uint32_t wd[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double d = rint(v[u]);
-            v[u] = (v[u] - d) * 128.0;
-            wd |= (uint32_t)((int)d & 0xff) << (8 * u);
-          }
-          *reinterpret_cast<uint32_t*>(tb + (size_t)s2 * TC_ATILE) = wd;
+        for (int u = 0; u < 16; ++u) {
+          const double d = rint(v[u]);
+          v[u] = (v[u] - d) * 128.0;
+          wd[u >> 2] |= (uint32_t)((int)d & 0xff) << (8 * (u & 3));
         }
+        *reinterpret_cast<uint4*>(tb + (size_t)s2 * TC_ATILE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
       }
     }
-  }
+  };
+  // CTAs that hold rows of the next diagonal block update and publish them first (the next leaf is waiting for them) and
+  // emit their planes afterwards; everybody else emits while waiting for X_top
+  const bool critical = fu.C && r0 < (int64_t)NB;
+  if (!critical) emit_planes();
   if (!fu.C) return;
   // ---- C[own rows, 0:uc] -= X[own rows, 0:nb] X_top[0:uc, 0:nb]^T
   {
@@ -664,6 +677,7 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
       }
     }
   }
+  if (critical) emit_planes();
 }
 
 static size_t panel_smem_bytes(bool fused = false) {
@@ -714,7 +728,7 @@ static inline int64_t split_point(int64_t n) { return ((n / NB + 1) / 2) * NB; }
 // Updates with K below this use the DMMA kernel (slicing + epilogue overhead of the int8 path); GPK_TC_MIN_K overrides.
 static int64_t tc_min_k() {
   static int64_t v = 0;
-  if (!v) { const char* e = getenv("GPK_TC_MIN_K"); v = e ? atoll(e) : 512; if (v < 128) v = 128; }
+  if (!v) { const char* e = getenv("GPK_TC_MIN_K"); v = e ? atoll(e) : 256; if (v < 128) v = 128; }
   return v;
 }
 

@@ -257,7 +257,7 @@ __global__ void logdensity_rows_kernel(const T* __restrict__ Fmu, const T* __res
 
 int logdensity_rows_impl(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P, double noise, void* out,
                          int dtype, cudaStream_t st) {
-  GPK_CHECK_ARG(noise > 0.0, "predict_log_density: noise variance must be positive");
+  GPK_CHECK_ARG(noise >= 0.0, "predict_log_density: noise variance must not be negative");
   GPK_CHECK_ARG(Fmu && Fvar && Y && out, "predict_log_density: null argument");
   if (B <= 0 || P <= 0) return 0;
   const unsigned g = (unsigned)((B + 255) / 256);

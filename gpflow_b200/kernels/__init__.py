@@ -1,8 +1,10 @@
 """gpflow.kernels surface for the hot path (RBF / Matern / Linear / White / Constant, Sum / Product,
 independent multi-output wrappers)."""
-from .base import Combination, Kernel, Product, ReducingCombination, Sum, compile_kernel
+from .base import Combination, Kernel, Product, ReducingCombination, Sum, compile_kernel, kernel_matrix
 from .linears import Linear, Polynomial
-from .multioutput import MultioutputKernel, SeparateIndependent, SharedIndependent
+from .materialised import AnisotropicStationary, ArcCosine, ChangePoints, Coregion, Cosine, Periodic
+from .multioutput import (IndependentLatent, LinearCoregionalization, MultioutputKernel, SeparateIndependent,
+                          SharedIndependent)
 from .statics import Bias, Constant, Static, White
 from .stationaries import (
     Exponential,
@@ -18,8 +20,8 @@ from .stationaries import (
 RBF = SquaredExponential
 
 __all__ = [
-    "Bias", "Combination", "Constant", "Exponential", "IsotropicStationary", "Kernel", "Linear", "Matern12", "Polynomial",
+    "AnisotropicStationary", "ArcCosine", "Bias", "ChangePoints", "Combination", "Coregion", "Cosine", "Periodic", "Constant", "Exponential", "IsotropicStationary", "IndependentLatent", "Kernel", "Linear", "LinearCoregionalization", "Matern12", "Polynomial",
     "Matern32", "Matern52", "MultioutputKernel", "Product", "RBF", "RationalQuadratic", "ReducingCombination",
     "SeparateIndependent", "SharedIndependent", "SquaredExponential", "Static", "Stationary", "Sum", "White",
-    "compile_kernel",
+    "compile_kernel", "kernel_matrix",
 ]

@@ -78,11 +78,22 @@ class Kernel(Module, metaclass=abc.ABCMeta):
         if presliced:
             raise NotImplementedError("presliced=True is not supported: the fused builder slices per leaf")
         X = ops.to_device(X)
+        X2 = None if X2 is None else ops.to_device(X2)
+        if not self.is_fusable():
+            # a leaf that is not a function of a Gram term (kernels/materialised.py): children are evaluated one by one
+            # and combined with elementwise device ops, as the reference composes them (base.py:281-314)
+            return self._materialise(X, X2, full_cov)
         desc = compile_kernel(self, X.shape[-1])
         if not full_cov:
             return ops.kdiag(desc, X)
-        X2 = None if X2 is None else ops.to_device(X2)
         return ops.kbuild(desc, X, X2)
+
+    def is_fusable(self) -> bool:
+        """True when the whole expression compiles into ONE fused K-build (every leaf has a `gpk_knode` record)."""
+        return True
+
+    def _materialise(self, X, X2, full_cov: bool):
+        raise NotImplementedError(f"{type(self).__name__} has no materialised evaluation")
 
     def __add__(self, other: "Kernel") -> "Kernel":
         return Sum([self, other])
@@ -111,6 +122,25 @@ class Combination(Kernel):
             else:
                 self.kernels.append(k)
 
+    def is_fusable(self) -> bool:
+        return all(k.is_fusable() for k in self.kernels)
+
+    def _materialise(self, X, X2, full_cov: bool):
+        """Sum / Product with at least one materialised child (base.py:305-314): children one by one, fusable runs of
+        children still in one fused pass."""
+        fus = [k for k in self.kernels if k.is_fusable()]
+        parts = [k(X, X2, full_cov=full_cov) if full_cov else k(X, full_cov=False) for k in self.kernels if not k.is_fusable()]
+        if fus:
+            grp = fus[0] if len(fus) == 1 else self.__class__(fus)
+            parts.append(grp(X, X2, full_cov=full_cov) if full_cov else grp(X, full_cov=False))
+        acc = parts[0]
+        for p in parts[1:]:
+            if self._op == _lib.K_SUM:
+                ops.axpby(1.0, p, 1.0, acc)
+            else:
+                ops.hadamard_(acc.view(acc.shape[0], -1), p.view(p.shape[0], -1))
+        return acc
+
     @property
     def on_separate_dimensions(self) -> bool:  # base.py:256-278
         if any(isinstance(k.active_dims, slice) for k in self.kernels):
@@ -133,6 +163,19 @@ class Sum(ReducingCombination):
 
 class Product(ReducingCombination):
     _op = _lib.K_PRODUCT
+
+
+def kernel_matrix(kernel: Kernel, X, X2=None, *, uplo: int = _lib.GPK_FULL, diag_scalar: float = 0.0, diag_vec=None):
+    """kernel(X, X2) [+ diag] on the device: ONE fused K-build when the expression compiles (then `uplo=LOWER` skips the
+    tiles above the diagonal), else the materialised evaluation (full matrix) followed by the diagonal shift."""
+    X = ops.to_device(X)
+    X2 = None if X2 is None else ops.to_device(X2)
+    if kernel.is_fusable():
+        return ops.kbuild(compile_kernel(kernel, X.shape[-1]), X, X2, uplo=uplo, diag_scalar=diag_scalar, diag_vec=diag_vec)
+    K = kernel(X, X2)
+    if diag_scalar != 0.0 or diag_vec is not None:
+        ops.add_diag_(K, diag_scalar, diag_vec)
+    return K
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 from .gpr import GPR
 from .model import BayesianModel, GPModel
-from .sgpr import SGPR
+from .sgpr import GPRFITC, SGPR
 from .svgp import SVGP
 from .vgp import VGP
 
@@ -13,5 +13,5 @@ def training_loss_closure(model, data=None, **kw):
     return model.training_loss_closure(**kw) if data is None else model.training_loss_closure(data, **kw)
 
 
-__all__ = ["BayesianModel", "GPModel", "GPR", "SGPR", "SVGP", "VGP", "maximum_log_likelihood_objective",
+__all__ = ["BayesianModel", "GPModel", "GPR", "GPRFITC", "SGPR", "SVGP", "VGP", "maximum_log_likelihood_objective",
            "training_loss_closure"]

@@ -46,17 +46,50 @@ class GPR(GPModel, InternalDataTrainingLossMixin):
         N, D = X.shape
         P = Y.shape[1]
         dc = ops.dtype_code(X)
+        Yc = self._centred_targets()
+        if self.likelihood.heteroskedastic:   # per-point noise (scalar_continuous.py:92-111; model_utils.py:33-50)
+            s2, svec = 0.0, self.likelihood.variance_at(X).reshape(-1).contiguous()
+        else:
+            s2, svec = self.likelihood._variance_value(), None
+        # a fresh result vector per call: earlier results stay valid when the model is evaluated again
+        self._out = ops.torch().empty((4,), dtype=ops.torch().float64, device=X.device)
+        if not self.kernel.is_fusable():
+            return self._lml_unfused(X, Yc, s2, svec)
         need = lib.gpk_gpr_lml_ws(N, P, dc)
         if self._ws is None or self._ws.numel() < need:
             self._ws = ops.scratch_bytes(need)
-        # a fresh result vector per call: earlier results stay valid when the model is evaluated again
-        self._out = ops.torch().empty((4,), dtype=ops.torch().float64, device=X.device)
         nodes, n_nodes, dims, ard = compile_kernel(self.kernel, D)
-        Yc = self._centred_targets()
-        _lib.check(lib.gpk_gpr_lml(nodes, n_nodes, dims, ard, ops._p(X), N, ops._ld(X), D, ops._p(Yc), P,
-                                   self.likelihood._variance_value(), None, dc, ops._p(self._out), ops._p(self._ws),
-                                   ops._stream()), "gpk_gpr_lml")
+        _lib.check(lib.gpk_gpr_lml(nodes, n_nodes, dims, ard, ops._p(X), N, ops._ld(X), D, ops._p(Yc), P, s2, ops._p(svec),
+                                   dc, ops._p(self._out), ops._p(self._ws), ops._stream()), "gpk_gpr_lml")
         return ops.objective(self._out, 0, 3)
+
+    def _lml_unfused(self, X, Yc, s2, svec):
+        """gpr.py:91-107 composed from the individual operators for kernels without a fused K-build record (Cosine,
+        Periodic, ArcCosine, Coregion, ChangePoints and combinations with them): K materialised, (Y - m)^T riding along
+        the factorisation as extra rows, the same reductions."""
+        import math
+        from ..kernels import kernel_matrix
+
+        T = ops.torch()
+        N, P = Yc.shape
+        A = ops.empty((N + P, N), like=X)
+        K = kernel_matrix(self.kernel, X, None, diag_scalar=s2, diag_vec=svec)
+        ops.axpby(1.0, K, 0.0, A[:N])
+        ops.transpose(Yc, out=A[N:])
+        info = T.empty((1,), dtype=T.int32, device=X.device)
+        lib = _lib.load()
+        ws = ops.scratch_bytes(lib.gpk_potrf_ws(N, N + P, ops.dtype_code(A)))
+        _lib.check(lib.gpk_potrf(ops._p(A), N, N + P, ops._ld(A), ops.dtype_code(A), ops._p(info), ops._p(ws),
+                                 ops._stream()), "gpk_potrf")
+        out = self._out
+        ops.fill(out.view(1, 4), 0.0)
+        ops.reduce(ops.SUMSQ, A[N:], N * P, 1, out=out[1:2], accumulate=True)            # sum alpha^2
+        ops.reduce(ops.SUMLOG, A, N, ops._ld(A) + 1, out=out[2:3], accumulate=True)       # sum log diag L
+        ops.axpby(-0.5, out[1:2], 0.0, out[0:1])
+        ops.axpby(-float(P), out[2:3], 1.0, out[0:1])
+        ops.axpby(1.0, ops.full((1,), -0.5 * N * P * math.log(2.0 * math.pi), dtype="float64"), 1.0, out[0:1])
+        self._info = info
+        return ops.objective(out, 0, None, info_tensor=info)
 
     def log_marginal_likelihood_and_grad(self):
         """Value and gradient in ONE fused call (gpk_gpr_lml_grad): the backward pass the reference gets from TensorFlow
@@ -111,6 +144,8 @@ class GPR(GPModel, InternalDataTrainingLossMixin):
 
     def cholesky_info(self) -> int:
         """0, or the 1-based index of the first non-positive pivot of the last evaluation."""
+        if getattr(self, "_info", None) is not None and not self.kernel.is_fusable():
+            return int(self._info.item())
         return int(self._out[3].item()) if self._out is not None else 0
 
     def posterior(self, precompute_cache=posteriors.PrecomputeCacheType.TENSOR) -> posteriors.GPRPosterior:

@@ -54,6 +54,26 @@ class GPModel(BayesianModel):
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):
         raise NotImplementedError
 
+    def predict_f_samples(self, Xnew, num_samples: Optional[int] = None, full_cov: bool = True,
+                          full_output_cov: bool = False, *, eps=None, generator=None):
+        """model.py:232-288: samples of the posterior latent function(s) at Xnew, [N, P] or [S, N, P].  `eps` injects the
+        standard-normal draws (shapes of conditionals.sample_mvn)."""
+        from ..conditionals import sample_mvn
+
+        if full_cov and full_output_cov:
+            raise NotImplementedError("The combination of both `full_cov` and `full_output_cov` is not supported.")
+        Xnew = ops.to_device(Xnew)
+        mean, cov = self.predict_f(Xnew, full_cov=full_cov, full_output_cov=full_output_cov)
+        if full_cov:                                                       # model.py:273-279
+            samples = sample_mvn(ops.transpose(mean), cov, True, num_samples, eps=eps, generator=generator)  # [(S), P, N]
+            if num_samples is None:
+                return ops.transpose(samples)
+            out = ops.empty((samples.shape[0], samples.shape[2], samples.shape[1]), like=samples)
+            for s_ in range(samples.shape[0]):
+                ops.transpose(samples[s_], out=out[s_])
+            return out
+        return sample_mvn(mean, cov, full_output_cov, num_samples, eps=eps, generator=generator)       # model.py:281-284
+
     def predict_y(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):  # model.py:290-325
         if full_cov or full_output_cov:
             raise NotImplementedError("The predict_y method currently supports only the argument values "

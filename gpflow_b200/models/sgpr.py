@@ -164,3 +164,92 @@ class SGPR(GPModel, InternalDataTrainingLossMixin):
     def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):  # sgpr.py:568-581
         return self.posterior(posteriors.PrecomputeCacheType.NOCACHE).fused_predict_f(
             Xnew, full_cov=full_cov, full_output_cov=full_output_cov)
+
+
+class GPRFITC(SGPR):
+    """GP regression with the FITC approximation (mirrors gpflow/models/sgpr.py:380-523; Snelson & Ghahramani 2006), a
+    re-composition of the same device operators: K-build (Kdiag, Kuf, Kuu), two Cholesky factorisations, triangular
+    solves, and fp64 reductions.  Same constructor as SGPR."""
+
+    def common_terms(self):
+        """sgpr.py:399-432 -> (err [N, R], nu [N], Luu [M, M], L [M, M], alpha [M, R], beta [N, R], gamma [M, R]) plus the
+        block inverses of the two factors (for the solves of predict_f)."""
+        X, Y = self.data
+        iv = self.inducing_variable
+        M = iv.num_inducing
+        err = Y if isinstance(self.mean_function, Zero) else ops.axpby(-1.0, self.mean_function(X), 1.0, ops.copy(Y))
+        Kdiag = self.kernel(X, full_cov=False)
+        kuf = covariances.Kuf(iv, self.kernel, X)
+        kuu = covariances.Kuu(iv, self.kernel, jitter=config.default_jitter())
+        sigma_sq = self.likelihood.variance_at(X).reshape(-1)
+        Luu, dinv_uu = ops.potrf(kuu)
+        ops.tril_(Luu)
+        V = ops.trsm(Luu, kuf, dinv=dinv_uu)                                  # V^T V = Qff
+        nu = ops.copy(Kdiag)                                                    # nu = Kdiag - diagQff + sigma_sq
+        ops.colsumsq(V, scale=-1.0, out=nu, accumulate=True)
+        ops.axpby(1.0, sigma_sq, 1.0, nu)
+        Vn = ops.scale_cols_(ops.copy(V), nu, invert=True)                      # V / nu
+        B = ops.gemm(Vn, V, transb=True)
+        ops.add_diag_(B, 1.0)
+        L, dinv_b = ops.potrf(B)
+        ops.tril_(L)
+        beta = ops.scale_rows_(ops.copy(err), nu, invert=True)                  # err / nu[:, None]
+        alpha = ops.gemm(V, beta)
+        gamma = ops.trsm(L, ops.copy(alpha), dinv=dinv_b)
+        self._dinvs = (dinv_uu, dinv_b)
+        return err, nu, Luu, L, alpha, beta, gamma
+
+    def maximum_log_likelihood_objective(self):  # sgpr.py:434-435
+        return self.fitc_log_marginal_likelihood()
+
+    def elbo(self):
+        raise NotImplementedError("GPRFITC optimises fitc_log_marginal_likelihood(), not an ELBO")
+
+    def fitc_log_marginal_likelihood(self):
+        """sgpr.py:440-480; device fp64 scalar."""
+        import math
+
+        err, nu, _Luu, L, _alpha, beta, gamma = self.common_terms()
+        N, R = err.shape
+        M = L.shape[0]
+        acc = ops.zeros_scalar(1)
+        # mahalanobis: -1/2 sum err^2 / nu + 1/2 sum gamma^2   (err^2 / nu = err * beta)
+        prod = ops.hadamard_(ops.copy(err), beta)
+        ops.reduce(ops.SUM, prod, N * R, 1, scale=-0.5, out=acc, accumulate=True)
+        ops.reduce(ops.SUMSQ, gamma, M * R, 1, scale=0.5, out=acc, accumulate=True)
+        # (constant + log-determinant) * num_latent_gps
+        P = float(self.num_latent_gps)
+        ops.reduce(ops.SUMLOG, nu, N, 1, scale=-0.5 * P, out=acc, accumulate=True)
+        ops.reduce(ops.SUMLOG, L, M, ops._ld(L) + 1, scale=-P, out=acc, accumulate=True)
+        ops.axpby(1.0, ops.full((1,), -0.5 * self.num_data * math.log(2.0 * math.pi) * P, dtype="float64"), 1.0, acc)
+        return acc[0]
+
+    def predict_f(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):  # sgpr.py:482-523
+        if full_output_cov:
+            raise NotImplementedError("GPRFITC.predict_f does not support full_output_cov=True")
+        _, _, Luu, L, _, _, gamma = self.common_terms()
+        dinv_uu, dinv_b = self._dinvs
+        Xnew = ops.to_device(Xnew)
+        Kus = covariances.Kuf(self.inducing_variable, self.kernel, Xnew)       # [M, N]
+        w = ops.trsm(Luu, Kus, dinv=dinv_uu)
+        tmp = ops.trsm(L, ops.copy(gamma), trans=True, dinv=dinv_b)             # L^-T gamma
+        mean = ops.gemm(w, tmp, transa=True)
+        if not isinstance(self.mean_function, Zero):
+            ops.axpby(1.0, self.mean_function(Xnew), 1.0, mean)
+        iA = ops.trsm(L, ops.copy(w), dinv=dinv_b)
+        P = self.num_latent_gps
+        if full_cov:
+            v = ops.copy(self.kernel(Xnew))
+            ops.gemm(w, w, transa=True, alpha=-1.0, beta=1.0, out=v)
+            ops.gemm(iA, iA, transa=True, alpha=1.0, beta=1.0, out=v)
+            var = ops.empty((P,) + tuple(v.shape), like=v)
+            for p in range(P):
+                ops.axpby(1.0, v, 0.0, var[p])
+            return mean, var
+        v = ops.copy(self.kernel(Xnew, full_cov=False))
+        ops.colsumsq(w, scale=-1.0, out=v, accumulate=True)
+        ops.colsumsq(iA, scale=1.0, out=v, accumulate=True)
+        var_t = ops.empty((P, v.shape[0]), like=v)
+        for p in range(P):
+            ops.axpby(1.0, v, 0.0, var_t[p])
+        return mean, ops.transpose(var_t)

@@ -63,6 +63,13 @@ class SVGP(GPModel, ExternalDataTrainingLossMixin):
         `batch_total=B` says that `data` holds only some ROWS of a minibatch of B rows (the data term is a sum over
         rows rescaled by num_data / B, svgp.py:173-181) and `include_kl=False` leaves the KL to another rank;
         in both cases the shares of all ranks sum to the full ELBO."""
+        if isinstance(self.kernel, MultioutputKernel) or not self.kernel.is_fusable() or \
+                not isinstance(self.likelihood, Gaussian) or self.likelihood.heteroskedastic:
+            # multi-output / materialised kernels: composed from the public operators exactly as the reference composes
+            # them (prior_kl, the posterior's predict_f, variational_expectations; svgp.py:166-181)
+            if latent_range is not None or batch_total is not None or not include_kl:
+                raise NotImplementedError("sharding options cover the fused single-output evaluation")
+            return self.elbo_unfused(data)
         out = self._fused(data, latent_range, 0, None, batch_total)
         if include_kl:
             return ops.objective(out, 0, 3)

@@ -123,7 +123,7 @@ class NonPositiveDefiniteError(_lib.GpkError):
 _OBJECTIVE_CLS = None
 
 
-def objective(out, value_idx: int = 0, info_idx: Optional[int] = None):
+def objective(out, value_idx: int = 0, info_idx: Optional[int] = None, info_tensor=None):
     """Scalar result of a fused objective: the 0-d DEVICE tensor out[value_idx] (no synchronisation), typed so that
     reading it on the host -- float(v), v.item(), v.cpu() -- also reads out[info_idx] in the same transfer and raises
     NonPositiveDefiniteError when the factorisation inside the evaluation met a non-positive pivot, as
@@ -142,11 +142,11 @@ def objective(out, value_idx: int = 0, info_idx: Optional[int] = None):
                 src = getattr(self, "_gpk_out", None)
                 if src is None:
                     return T.Tensor.item(self.as_subclass(T.Tensor))
-                out_, vi, ii = src
+                out_, vi, ii, it = src
                 h = out_.cpu()
-                if ii is not None and int(h[ii]) != 0:
-                    raise NonPositiveDefiniteError(
-                        f"Cholesky decomposition was not successful (pivot {int(h[ii])} <= 0)")
+                piv = int(h[ii]) if ii is not None else (int(it.cpu()[0]) if it is not None else 0)
+                if piv != 0:
+                    raise NonPositiveDefiniteError(f"Cholesky decomposition was not successful (pivot {piv} <= 0)")
                 return float(h[vi])
 
             def item(self):
@@ -161,7 +161,7 @@ def objective(out, value_idx: int = 0, info_idx: Optional[int] = None):
 
         _OBJECTIVE_CLS = Objective
     v = out[value_idx].as_subclass(_OBJECTIVE_CLS)
-    v._gpk_out = (out, value_idx, info_idx)
+    v._gpk_out = (out, value_idx, info_idx, info_tensor)
     return v
 
 
@@ -271,6 +271,15 @@ def axpby(a: float, X, b: float, Y):
         (m, n), ldx, ldy = X.shape, _ld(X), _ld(Y)
     check(_lib.load().gpk_axpby(m, n, float(a), _p(X), ldx, float(b), _p(Y), ldy, dtype_code(X), _stream()),
           "gpk_axpby")
+    return Y
+
+
+def hadamard_(Y, X):
+    """Y *= X elementwise (2-D, same shape)."""
+    if tuple(X.shape) != tuple(Y.shape) or X.dim() != 2:
+        raise ValueError(f"hadamard_: shapes {tuple(X.shape)} and {tuple(Y.shape)} do not match")
+    check(_lib.load().gpk_hadamard(X.shape[0], X.shape[1], _p(X), _ld(X), _p(Y), _ld(Y), dtype_code(X), _stream()),
+          "gpk_hadamard")
     return Y
 
 

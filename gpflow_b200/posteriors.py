@@ -111,11 +111,13 @@ class GPRPosterior(AbstractPosterior):
         err = ops.copy(self.Y_data)
         if self.mean_function is not None and not isinstance(self.mean_function, Zero):
             ops.axpby(-1.0, self.mean_function(self.X_data), 1.0, err)
-        from .kernels import compile_kernel
+        from .kernels import kernel_matrix
 
-        desc = compile_kernel(self.kernel, self.X_data.shape[1])
-        Kmm = ops.kbuild(desc, self.X_data, None, uplo=_lib.GPK_LOWER,
-                         diag_scalar=self.likelihood._variance_value())
+        if self.likelihood.heteroskedastic:  # add_noise_cov with the per-point variance (model_utils.py:33-50)
+            s2, svec = 0.0, self.likelihood.variance_at(self.X_data).reshape(-1)
+        else:
+            s2, svec = self.likelihood._variance_value(), None
+        Kmm = kernel_matrix(self.kernel, self.X_data, None, uplo=_lib.GPK_LOWER, diag_scalar=s2, diag_vec=svec)
         Lm, dinv = ops.potrf(Kmm)
         ops.tril_(Lm)
         return err, Lm, dinv
@@ -297,10 +299,141 @@ def _get_posterior_base_case(kernel: Kernel, inducing_variable: InducingVariable
     return IndependentPosteriorSingleOutput  # posteriors.py:1042-1047
 
 
+class IndependentPosteriorMultiOutput(IndependentPosterior):
+    """posteriors.py:844-885: L independent latent GPs; the kernel and / or the inducing variables may be shared.
+    fmean [N, L]; fvar [N, L] (full_cov=False) or [L, N, N] (full_cov=True).  full_output_cov=True expands the
+    independent outputs to (block-)diagonal form (conditionals/util.py:222-254)."""
+
+    def _latents(self):
+        return covariances._latent_pairs(self.X_data, self.kernel)
+
+    def _conditional_fused(self, Xnew, full_cov: bool = False, full_output_cov: bool = False):
+        from .inducing_variables import FallbackSharedIndependentInducingVariables
+        from .kernels import SharedIndependent
+
+        q_mu, q_sqrt = self.q_mu, self.q_sqrt
+        if isinstance(self.X_data, FallbackSharedIndependentInducingVariables) and isinstance(self.kernel, SharedIndependent):
+            Knn = self.kernel.kernel(Xnew, full_cov=full_cov)                     # :851-860: one factorisation for all
+            Kmm = covariances.Kuu(self.X_data, self.kernel, jitter=config.default_jitter())
+            Kmn = covariances.Kuf(self.X_data, self.kernel, Xnew)
+            Lm, dinv = ops.potrf(Kmm)
+            ops.tril_(Lm)
+            fmean, fvar = base_conditional_with_lm(Kmn, Lm, Knn, q_mu, full_cov=full_cov, q_sqrt=q_sqrt,
+                                                   white=self.whiten, dinv=dinv)
+        else:                                                                     # :861-882, one latent at a time
+            pairs = self._latents()
+            L, N = len(pairs), Xnew.shape[0]
+            fmean_t = ops.empty((L, N), like=Xnew)
+            fvar = ops.empty((L, N, N), like=Xnew) if full_cov else None
+            fvar_t = None if full_cov else ops.empty((L, N), like=Xnew)
+            for l, (iv, k) in enumerate(pairs):
+                Kmm = covariances.Kuu(iv, k, jitter=config.default_jitter())
+                Kmn = covariances.Kuf(iv, k, Xnew)
+                Knn = k(Xnew, full_cov=full_cov)
+                Lm, dinv = ops.potrf(Kmm)
+                ops.tril_(Lm)
+                qs = None if q_sqrt is None else (ops.copy(q_sqrt[:, l:l + 1]) if q_sqrt.dim() == 2 else q_sqrt[l:l + 1])
+                m_l, v_l = base_conditional_with_lm(Kmn, Lm, Knn, ops.copy(q_mu[:, l:l + 1]), full_cov=full_cov, q_sqrt=qs,
+                                                    white=self.whiten, dinv=dinv)
+                ops.axpby(1.0, m_l.reshape(-1), 0.0, fmean_t[l])
+                if full_cov:
+                    ops.axpby(1.0, v_l[0], 0.0, fvar[l])
+                else:
+                    ops.axpby(1.0, v_l.reshape(-1), 0.0, fvar_t[l])
+            fmean = ops.transpose(fmean_t)
+            if not full_cov:
+                fvar = ops.transpose(fvar_t)
+        return self._post_process_mean_and_cov(fmean, fvar, full_cov, full_output_cov)
+
+    def _conditional_with_precompute(self, cache, Xnew, full_cov: bool = False, full_output_cov: bool = False):
+        return self._conditional_fused(Xnew, full_cov=full_cov, full_output_cov=full_output_cov)
+
+    def _precompute(self):
+        return ()   # the per-latent factorisations are redone per call (cache type semantics kept: results identical)
+
+    def _post_process_mean_and_cov(self, mean, cov, full_cov: bool, full_output_cov: bool):
+        return mean, expand_independent_outputs(cov, full_cov, full_output_cov)
+
+
+def expand_independent_outputs(fvar, full_cov: bool, full_output_cov: bool):
+    """conditionals/util.py:222-254: [N, P] -> [N, P, P] / [P, N, N] -> [N, P, N, P] (diagonal over the outputs) when
+    full_output_cov, identity otherwise."""
+    if not full_output_cov:
+        return fvar
+    if full_cov:
+        P, N = fvar.shape[0], fvar.shape[1]
+        # block-diagonal in a [(p, n), (p', n')]-ordered buffer, then reordered to [n, p, n', p']
+        buf = ops.full((P * N, P * N), 0.0, like=fvar)                 # rows (p, n), cols (p', n')
+        for p in range(P):
+            ops.axpby(1.0, fvar[p], 0.0, buf[p * N:(p + 1) * N, p * N:(p + 1) * N])
+        return _pnpn_to_npnp(buf, P, N)
+    N, P = fvar.shape
+    out = ops.full((N, P * P), 0.0, like=fvar)
+    for p in range(P):
+        ops.axpby(1.0, fvar[:, p:p + 1], 0.0, out[:, p * P + p:p * P + p + 1])
+    return out.view(N, P, P)
+
+
+def _pnpn_to_npnp(buf, P: int, N: int):
+    """[(p, n), (p', n')] -> [n, p, n', p'] with two blocked transpositions (rows, then columns)."""
+    out = ops.empty((N * P, N * P), like=buf)
+    tmp = ops.empty((N * P, N * P), like=buf)
+    for p in range(P):          # rows: (p, n) -> (n, p)
+        ops.axpby(1.0, buf[p * N:(p + 1) * N, :], 0.0, tmp[p::P, :])
+    tmp_t = ops.transpose(tmp)  # now rows are (p', n')
+    out_t = ops.empty((N * P, N * P), like=buf)
+    for p in range(P):
+        ops.axpby(1.0, tmp_t[p * N:(p + 1) * N, :], 0.0, out_t[p::P, :])
+    return ops.transpose(out_t, out=out).view(N, P, N, P)
+
+
+class LinearCoregionalizationPosterior(IndependentPosteriorMultiOutput):
+    """posteriors.py:888-901: the latent posteriors mixed by W, f = W g (conditionals/util.py:518-563)."""
+
+    def _post_process_mean_and_cov(self, mean, cov, full_cov: bool, full_output_cov: bool):
+        import numpy as np
+
+        W = np.asarray(self.kernel.W.numpy(), dtype=np.float64)              # [P, L]
+        P, L = W.shape
+        Wd = ops.to_device(W)
+        f_mean = ops.gemm(mean, Wd, transb=True)                               # [N, P]
+        if not full_cov and not full_output_cov:
+            return f_mean, ops.gemm(cov, ops.to_device(W ** 2), transb=True)   # [N, L] x (W^2)^T
+        if not full_cov and full_output_cov:                                   # [N, P, P] = sum_l g_var[n, l] W[:, l] W[:, l]^T
+            outer = np.stack([np.outer(W[:, l], W[:, l]).reshape(-1) for l in range(L)])   # [L, P * P]
+            return f_mean, ops.gemm(cov, ops.to_device(outer)).view(cov.shape[0], P, P)
+        if full_cov and not full_output_cov:                                   # [P, N, N] = sum_l W[p, l]^2 g_var[l]
+            N = cov.shape[1]
+            out = ops.full((P, N, N), 0.0, like=cov)
+            for p in range(P):
+                for l in range(L):
+                    ops.axpby(float(W[p, l] ** 2), cov[l], 1.0, out[p])
+            return f_mean, out
+        N = cov.shape[1]                                                       # [N, P, N, P]
+        buf = ops.full((P * N, P * N), 0.0, like=cov)
+        for p in range(P):
+            for q in range(P):
+                blk = buf[p * N:(p + 1) * N, q * N:(q + 1) * N]
+                for l in range(L):
+                    ops.axpby(float(W[p, l] * W[q, l]), cov[l], 1.0, blk)
+        return f_mean, _pnpn_to_npnp(buf, P, N)
+
+
 @get_posterior_class.register(MultioutputKernel, InducingVariables)
 def _get_posterior_mo(kernel, inducing_variable):
-    raise NotImplementedError("multi-output SVGP posteriors (posteriors.py:844-1036) are outside the hot path; "
-                              "shard independent outputs over models instead")
+    from .inducing_variables import (FallbackSeparateIndependentInducingVariables,
+                                     FallbackSharedIndependentInducingVariables)
+    from .kernels import LinearCoregionalization, SeparateIndependent, SharedIndependent
+
+    if not isinstance(inducing_variable, (FallbackSharedIndependentInducingVariables,
+                                          FallbackSeparateIndependentInducingVariables)):
+        raise NotImplementedError("multi-output kernels need Shared/SeparateIndependentInducingVariables")
+    if isinstance(kernel, LinearCoregionalization):
+        return LinearCoregionalizationPosterior          # posteriors.py:1074-1086
+    if isinstance(kernel, (SharedIndependent, SeparateIndependent)):
+        return IndependentPosteriorMultiOutput           # posteriors.py:1050-1071
+    raise NotImplementedError("fully correlated multi-output posteriors (posteriors.py:904-1009) are not built: every "
+                              "kernel class of this package has independent latent GPs")
 
 
 def create_posterior(kernel: Kernel, inducing_variable: InducingVariables, q_mu, q_sqrt, whiten: bool,

@@ -182,6 +182,50 @@ GPK_API int gpk_gaussian_varexp_sum(const void* Fmu, const void* Fvar, const voi
 GPK_API int gpk_gaussian_log_density(const void* Fmu, const void* Fvar, const void* Y, int64_t B, int64_t P,
                              double noise_variance, void* out, int dtype, void* stream);
 
+/* ---- Kernels that are not functions of a Gram term (materialised leaves; the Python layer composes them with
+ * Sum / Product / ChangePoints through gpk_axpby / gpk_hadamard / gpk_scale_rows / gpk_scale_cols) ------------------ */
+enum {
+  GPK_KAUX_COSINE = 0,   /* sigma^2 cos(2 pi sum_d (x_d - x'_d) scale_d), scale = 1 / lengthscale   stationaries.py:316-332 */
+  GPK_KAUX_PERIODIC = 1, /* base.K_r(sum_d |sin(pi (x_d - x'_d) / period_d)| scale_d) for bases with K_r (Matern12/32/52,
+                            Exponential), base.K_r2(sum_d sin^2(...) scale_d^2) otherwise (RBF, RQ)    periodic.py:28-111 */
+  GPK_KAUX_ARCCOS = 2,   /* sigma^2 / pi J_order(theta) |x|^order |x'|^order, |x|^2 = sum_d scale_d x_d^2 + bias
+                            (scale = weight variances)                                               misc.py:27-200 */
+  GPK_KAUX_COREGION = 3  /* table[int(x), int(x')], table = W W^T + diag(kappa) [table_dim^2 doubles]  misc.py:203-296 */
+};
+#define GPK_KAUX_MAXD 32
+typedef struct gpk_kaux_desc {
+  int32_t op;
+  int32_t base;      /* PERIODIC: GPK_K_* op code of the base kernel */
+  int32_t order;     /* ARCCOS: 0, 1 or 2 */
+  int32_t n_dims;    /* active columns (explicit, 1..GPK_KAUX_MAXD) */
+  int32_t table_dim; /* COREGION: output_dim */
+  int32_t pad_;
+  double variance, alpha, bias;
+  const void* table; /* COREGION: DEVICE pointer to the [table_dim, table_dim] float64 matrix B */
+  int32_t dims[GPK_KAUX_MAXD];
+  double scale[GPK_KAUX_MAXD];
+  double period[GPK_KAUX_MAXD];
+} gpk_kaux_desc;
+
+/* K [N, N2] = kernel(X, X2) (X2 NULL: K(X, X)) and its diagonal for the kernels above. */
+GPK_API int gpk_kaux(const gpk_kaux_desc* desc, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2,
+             int64_t ldx2, void* K, int64_t ldk, int dtype, void* stream);
+GPK_API int gpk_kaux_diag(const gpk_kaux_desc* desc, const void* X, int64_t N, int64_t ldx, void* out, int dtype,
+                  void* stream);
+/* ChangePoints sigmoid weights (gpflow/kernels/changepoints.py:118-137,189-193): out[n] =
+ * (has_lo ? sig(steep_lo (x_n - loc_lo)) : 1) * (has_hi ? 1 - sig(steep_hi (x_n - loc_hi)) : 1), x_n = X[n, dim]. */
+GPK_API int gpk_changepoint_weights(const void* X, int64_t N, int64_t ldx, int dim, int has_lo, double loc_lo,
+                            double steep_lo, int has_hi, double loc_hi, double steep_hi, void* out,
+                            int dtype, void* stream);
+/* A[m, n] = max(A, lower), then squared (`square` = 1) or square-rooted (2): evaluation of a heteroskedastic
+ * Gaussian(variance|scale=Function) (gpflow/likelihoods/scalar_continuous.py:92-102: tf.maximum(f(X), lower_bound) [** 2])
+ * and tf.sqrt(cov) of sample_mvn (conditionals/util.py:199). */
+GPK_API int gpk_clamp_min(void* A, int64_t m, int64_t n, int64_t lda, double lower, int square, int dtype,
+                  void* stream);
+/* Y[m, n] *= X elementwise (Product of materialised kernels, base.py:311-314). */
+GPK_API int gpk_hadamard(int64_t m, int64_t n, const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype,
+                 void* stream);
+
 /* ---- Fused objectives: one call per evaluation ------------------------------------------- */
 
 /* GPR.log_marginal_likelihood (gpflow/models/gpr.py:91-107): K-build(lower)+noise, Cholesky with

@@ -260,6 +260,129 @@ class Product(Combination):
         return out
 
 
+def difference_matrix(X, X2):
+    """gpflow/utilities/ops.py:125-160 -> [N, N2, D]."""
+    X2 = X if X2 is None else X2
+    return X[:, None, :] - X2[None, :, :]
+
+
+class Cosine(Stationary):
+    """gpflow/kernels/stationaries.py:316-332 (AnisotropicStationary: K_d of the scaled per-dimension differences,
+    stationaries.py:133-196)."""
+
+    def K(self, X, X2=None):
+        d = difference_matrix(self.scale(X), self.scale(X2))
+        return self._c(self.variance, X) * np.cos(2 * np.pi * np.sum(d, axis=-1))
+
+
+class Periodic(Kernel):
+    """gpflow/kernels/periodic.py:28-111; uses the base kernel's active_dims."""
+
+    def __init__(self, base_kernel: Stationary, period=1.0):
+        super().__init__(None)
+        self.base_kernel = base_kernel
+        self.active_dims = base_kernel.active_dims
+        self.period = period
+
+    def K_diag(self, X):  # periodic.py:91-93
+        return self.base_kernel.K_diag(X)
+
+    def K(self, X, X2=None):  # periodic.py:95-111
+        r = np.pi * difference_matrix(X, X2) / np.asarray(self.period, dtype=X.dtype)
+        scaled_sine = np.sin(r) / np.asarray(self.base_kernel.lengthscales, dtype=X.dtype)
+        if hasattr(self.base_kernel, "K_r"):
+            return self.base_kernel.K_r(np.sum(np.abs(scaled_sine), -1))
+        return self.base_kernel.K_r2(np.sum(np.square(scaled_sine), -1))
+
+
+class ArcCosine(Kernel):
+    """gpflow/kernels/misc.py:27-200."""
+
+    def __init__(self, order=0, variance=1.0, weight_variances=1.0, bias_variance=1.0, active_dims=None):
+        super().__init__(active_dims)
+        if order not in (0, 1, 2):
+            raise ValueError("Requested kernel order is not implemented.")
+        self.order, self.variance, self.weight_variances, self.bias_variance = order, variance, weight_variances, bias_variance
+
+    def _diag_weighted_product(self, X):  # misc.py:88-89
+        return np.sum(np.asarray(self.weight_variances) * np.square(X), axis=-1) + self.bias_variance
+
+    def _J(self, theta):  # misc.py:141-157
+        if self.order == 0:
+            return np.pi - theta
+        if self.order == 1:
+            return np.sin(theta) + (np.pi - theta) * np.cos(theta)
+        return 3.0 * np.sin(theta) * np.cos(theta) + (np.pi - theta) * (1.0 + 2.0 * np.cos(theta) ** 2)
+
+    def K(self, X, X2=None):  # misc.py:160-194
+        Xd = np.sqrt(self._diag_weighted_product(X))
+        X2_ = X if X2 is None else X2
+        X2d = np.sqrt(self._diag_weighted_product(X2_))
+        num = (np.asarray(self.weight_variances) * X) @ X2_.T + self.bias_variance
+        cos_theta = num / Xd[:, None] / X2d[None, :]
+        jitter = 1e-15
+        theta = np.arccos(jitter + (1 - 2 * jitter) * cos_theta)
+        return self.variance * (1.0 / np.pi) * self._J(theta) * Xd[:, None] ** self.order * X2d[None, :] ** self.order
+
+    def K_diag(self, X):  # misc.py:197-200
+        return self.variance * (1.0 / np.pi) * self._J(0.0) * self._diag_weighted_product(X) ** self.order
+
+
+class Coregion(Kernel):
+    """gpflow/kernels/misc.py:203-296."""
+
+    def __init__(self, output_dim, rank, W=None, kappa=None, active_dims=None):
+        super().__init__(active_dims)
+        self.W = 0.1 * np.ones((output_dim, rank)) if W is None else np.asarray(W)
+        self.kappa = np.ones(output_dim) if kappa is None else np.asarray(kappa)
+
+    def output_covariance(self):
+        return self.W @ self.W.T + np.diag(self.kappa)
+
+    def K(self, X, X2=None):
+        B = self.output_covariance()
+        i = X[..., 0].astype(np.int32)
+        j = i if X2 is None else X2[..., 0].astype(np.int32)
+        return B[np.ix_(i, j)]
+
+    def K_diag(self, X):
+        return (np.sum(np.square(self.W), 1) + self.kappa)[X[..., 0].astype(np.int32)]
+
+
+class ChangePoints(Kernel):
+    """gpflow/kernels/changepoints.py:26-193 (1-D inputs)."""
+
+    def __init__(self, kernels, locations, steepness=1.0):
+        super().__init__(None)
+        self.kernels, self.locations = list(kernels), np.asarray(locations, dtype=np.float64)
+        self.steepness = steepness
+
+    def _sigmoids(self, X):  # changepoints.py:189-193
+        return 1.0 / (1.0 + np.exp(-np.asarray(self.steepness) * (X[:, :, None] - self.locations.reshape(1, 1, -1))))
+
+    def __call__(self, X, X2=None, *, full_cov=True, presliced=False):
+        return self.K(X, X2) if full_cov else self.K_diag(X)
+
+    def K(self, X, X2=None):  # changepoints.py:86-149
+        sig_X = self._sigmoids(X)[:, 0, :]                                      # [N, Ncp]
+        sig_X2 = sig_X if X2 is None else self._sigmoids(X2)[:, 0, :]
+        starters = sig_X[:, None, :] * sig_X2[None, :, :]
+        stoppers = (1 - sig_X)[:, None, :] * (1 - sig_X2)[None, :, :]
+        ones = np.ones(starters.shape[:2] + (1,), dtype=X.dtype)
+        starters = np.concatenate([ones, starters], axis=-1)
+        stoppers = np.concatenate([stoppers, ones], axis=-1)
+        stack = np.stack([k(X, X2) for k in self.kernels], axis=-1)
+        return np.sum(stack * starters * stoppers, axis=-1)
+
+    def K_diag(self, X):  # changepoints.py:152-176
+        sig = self._sigmoids(X)[:, 0, :]
+        ones = np.ones((X.shape[0], 1), dtype=X.dtype)
+        starters = np.concatenate([ones, sig * sig], axis=-1)
+        stoppers = np.concatenate([(1 - sig) * (1 - sig), ones], axis=-1)
+        stack = np.stack([k(X, full_cov=False) for k in self.kernels], axis=-1)
+        return np.sum(stack * starters * stoppers, axis=-1)
+
+
 class SeparateIndependent:
     """gpflow/kernels/multioutput/kernels.py:200-271, full_output_cov=False rows only."""
 
@@ -656,6 +779,99 @@ def svgp_predict_f_cached(Xnew, Z, kernel, alpha, Qinv, mean_function=None):
     mean = kuf.T @ alpha
     cov = Kff[None] - np.sum(kuf[None] * (Qinv @ kuf), axis=-2)
     return mean + _mean(mean_function, Xnew, alpha.shape[1]), cov.T
+
+
+# ----------------------------------------------------------------------------------------
+# sampling, FITC, multi-output posteriors
+# ----------------------------------------------------------------------------------------
+def sample_mvn(mean, cov, full_cov: bool, eps, jitter=DEFAULT_JITTER):
+    """gpflow/conditionals/util.py:179-211 with the standard-normal draws `eps` given ([S, N, D] when not full_cov,
+    [N, D, S] when full_cov) instead of tf.random.normal; returns [S, N, D]."""
+    if not full_cov:
+        return mean[None] + np.sqrt(cov)[None] * eps
+    D = mean.shape[-1]
+    chol = np.stack([cholesky(c + jitter * np.eye(D)) for c in cov])          # [N, D, D]
+    samples = mean[..., None] + chol @ eps                                    # [N, D, S]
+    return np.transpose(samples, (2, 0, 1))
+
+
+def predict_f_samples(mean, cov, full_cov: bool, eps, full_output_cov=False, jitter=DEFAULT_JITTER):
+    """gpflow/models/model.py:267-288 given predict_f's (mean [N, P], cov); [S, N, P]."""
+    if full_cov:
+        s = sample_mvn(mean.T, cov, True, eps, jitter)                        # [S, P, N]
+        return np.transpose(s, (0, 2, 1))
+    return sample_mvn(mean, cov, full_output_cov, eps, jitter)
+
+
+def gprfitc_common(X, Y, kernel, Z, noise_variance, mean_function=None, jitter=DEFAULT_JITTER):
+    """gpflow/models/sgpr.py:399-432."""
+    err = Y - _mean(mean_function, X, Y.shape[1])
+    Kdiag = kernel(X, full_cov=False)
+    kuf = Kuf(Z, kernel, X)
+    kuu = Kuu(Z, kernel, jitter=jitter)
+    sigma_sq = np.broadcast_to(np.asarray(noise_variance, dtype=X.dtype), (X.shape[0],))
+    Luu = cholesky(kuu)
+    V = tri_solve(Luu, kuf)
+    nu = Kdiag - np.sum(np.square(V), 0) + sigma_sq
+    B = np.eye(Z.shape[0], dtype=X.dtype) + (V / nu) @ V.T
+    L = cholesky(B)
+    beta = err / nu[:, None]
+    alpha = V @ beta
+    gamma = tri_solve(L, alpha)
+    return err, nu, Luu, L, alpha, beta, gamma
+
+
+def gprfitc_lml(X, Y, kernel, Z, noise_variance, mean_function=None, jitter=DEFAULT_JITTER) -> float:
+    """gpflow/models/sgpr.py:440-480."""
+    err, nu, _, L, _, _, gamma = gprfitc_common(X, Y, kernel, Z, noise_variance, mean_function, jitter)
+    maha = -0.5 * np.sum(np.square(err) / nu[:, None]) + 0.5 * np.sum(np.square(gamma))
+    const = -0.5 * X.shape[0] * np.log(2.0 * np.pi)
+    logdet = -0.5 * np.sum(np.log(nu)) - np.sum(np.log(np.diag(L)))
+    return float(maha + (const + logdet) * Y.shape[1])
+
+
+def gprfitc_predict_f(X, Y, kernel, Z, noise_variance, Xnew, mean_function=None, full_cov=False, jitter=DEFAULT_JITTER):
+    """gpflow/models/sgpr.py:482-523."""
+    _, _, Luu, L, _, _, gamma = gprfitc_common(X, Y, kernel, Z, noise_variance, mean_function, jitter)
+    Kus = Kuf(Z, kernel, Xnew)
+    w = tri_solve(Luu, Kus)
+    tmp = tri_solve(L, gamma, trans=True)
+    mean = w.T @ tmp + _mean(mean_function, Xnew, Y.shape[1])
+    iA = tri_solve(L, w)
+    P = Y.shape[1]
+    if full_cov:
+        var = kernel(Xnew) - w.T @ w + iA.T @ iA
+        return mean, np.tile(var[None], (P, 1, 1))
+    var = kernel(Xnew, full_cov=False) - np.sum(np.square(w), 0) + np.sum(np.square(iA), 0)
+    return mean, np.tile(var[:, None], (1, P))
+
+
+def mo_independent_predict_f(Xnew, Zs, kernels, q_mu, q_sqrt, *, whiten=True, full_cov=False, jitter=DEFAULT_JITTER):
+    """gpflow/posteriors.py:844-885 / conditionals/util.py:566-629: L independent latent GPs, latent l with inducing
+    inputs Zs[l] and kernel kernels[l] (lists of length 1 are shared).  fmean [N, L]; fvar [N, L] or [L, N, N]."""
+    L = q_mu.shape[1]
+    means, vars_ = [], []
+    for l in range(L):
+        Z = Zs[l if len(Zs) > 1 else 0]
+        k = kernels[l if len(kernels) > 1 else 0]
+        qs = None if q_sqrt is None else (q_sqrt[:, l:l + 1] if q_sqrt.ndim == 2 else q_sqrt[l:l + 1])
+        m, v = base_conditional(Kuf(Z, k, Xnew), Kuu(Z, k, jitter=jitter), k(Xnew, full_cov=full_cov), q_mu[:, l:l + 1],
+                                full_cov=full_cov, q_sqrt=qs, white=whiten)
+        means.append(m[:, 0])
+        vars_.append(v[0] if full_cov else v[:, 0])
+    return np.stack(means, 1), (np.stack(vars_, 0) if full_cov else np.stack(vars_, 1))
+
+
+def mix_latent_gp(W, g_mean, g_var, full_cov: bool, full_output_cov: bool):
+    """gpflow/conditionals/util.py:518-563; W [P, L]."""
+    f_mean = g_mean @ W.T
+    if full_cov and full_output_cov:        # g_var [L, N, N] -> [N, P, N, P]
+        return f_mean, np.einsum("lnm,pl,ql->npmq", g_var, W, W)
+    if full_cov:                            # -> [P, N, N]
+        return f_mean, np.einsum("lnm,pl->pnm", g_var, W ** 2)
+    if full_output_cov:                     # g_var [N, L] -> [N, P, P]
+        return f_mean, np.einsum("nl,pl,ql->npq", g_var, W, W)
+    return f_mean, g_var @ (W ** 2).T
 
 
 # ----------------------------------------------------------------------------------------

@@ -419,3 +419,89 @@ def test_conditional_diag_q_sqrt_equals_cholesky_q_sqrt(white):
     m2, v2 = O.base_conditional(Kmn, Kmm, Knn, mu, q_sqrt=chol, white=white)
     np.testing.assert_allclose(m1, m2, atol=1e-12)
     np.testing.assert_allclose(v1, v2, atol=1e-12)
+
+
+# ---- kernels widened in round 2 (restating the reference's own checks) -----------------------------------------------
+def test_periodic_reduces_to_base_on_mapped_inputs_and_cosine_identity():
+    """gpflow/kernels/periodic.py docstring: the periodic kernel is the base kernel on u = (cos x, sin x); for the
+    SquaredExponential base sum_d sin^2(pi (x - x') / p) / l^2 = |u - u'|^2 / (4 l^2) with u at angle 2 pi x / p.
+    Cosine: cos(2 pi (a - b)) = cos 2 pi a cos 2 pi b + sin 2 pi a sin 2 pi b (a rank-2 kernel, so PSD)."""
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((9, 2))
+    p, ell = np.array([1.5, 0.7]), 0.9
+    kper = O.Periodic(O.SquaredExponential(1.3, ell), p)
+    ang = 2 * np.pi * X / p
+    U = np.concatenate([np.cos(ang), np.sin(ang)], axis=1)
+    d2 = ((U[:, None, :] - U[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(kper(X), 1.3 * np.exp(-0.5 * d2 / (4 * ell ** 2)), rtol=1e-12)
+    kc = O.Cosine(0.8, [0.5, 2.0])
+    a = (X / np.array([0.5, 2.0])).sum(1)
+    ref = 0.8 * (np.outer(np.cos(2 * np.pi * a), np.cos(2 * np.pi * a)) + np.outer(np.sin(2 * np.pi * a), np.sin(2 * np.pi * a)))
+    np.testing.assert_allclose(kc(X), ref, rtol=1e-10, atol=1e-12)
+
+
+def test_arccosine_changepoints_coregion_symmetric_psd_and_diag():
+    """tests/gpflow/kernels/test_kernels.py: symmetric, PSD, K_diag == diag(K) (ArcCosine orders 0-2;
+    ChangePoints with steep sigmoids switches between its regimes; Coregion indexes B = W W^T + diag(kappa))."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((20, 3))
+    for order in (0, 1, 2):
+        k = O.ArcCosine(order, 1.1, [0.5, 1.5, 1.0], 0.7)
+        Km = k(X)
+        np.testing.assert_allclose(Km, Km.T, rtol=1e-12)
+        assert np.linalg.eigvalsh(Km).min() > -1e-8
+        np.testing.assert_allclose(np.diag(Km), k(X, full_cov=False), rtol=1e-6)  # acos near 1 (jitter 1e-15)
+    x = np.linspace(0, 1, 30)[:, None]
+    cp = O.ChangePoints([O.SquaredExponential(1.0, 0.3), O.Matern32(2.0, 0.2)], [0.5], 1e4)
+    Km = cp(x)
+    lo, hi = x[:, 0] < 0.49, x[:, 0] > 0.51
+    np.testing.assert_allclose(Km[np.ix_(lo, lo)], O.SquaredExponential(1.0, 0.3)(x[lo]), atol=1e-9)
+    np.testing.assert_allclose(Km[np.ix_(hi, hi)], O.Matern32(2.0, 0.2)(x[hi]), atol=1e-9)
+    np.testing.assert_allclose(Km[np.ix_(lo, hi)], 0.0, atol=1e-9)
+    W = rng.standard_normal((4, 2))
+    cg = O.Coregion(4, 2, W=W, kappa=np.array([1.0, 2.0, 0.5, 0.1]))
+    idx = np.array([[3.0], [0.0], [3.0], [1.0]])
+    B = W @ W.T + np.diag([1.0, 2.0, 0.5, 0.1])
+    np.testing.assert_allclose(cg(idx), B[np.ix_([3, 0, 3, 1], [3, 0, 3, 1])], rtol=1e-14)
+
+
+def test_fitc_equals_gpr_when_inducing_points_are_the_data_and_mixing_identities():
+    """tests/gpflow/models/test_sgpr.py / test_method_equivalence.py idea: with Z = X the FITC approximation is exact
+    (nu = sigma^2 up to the jitter), so its LML and predictions equal GPR's.  mix_latent_gp with W = I is the identity,
+    and its full covariance contracts to the marginal forms."""
+    rng = np.random.default_rng(6)
+    X = rng.standard_normal((30, 2))
+    Y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((30, 2))
+    k = O.Matern32(1.2, 0.9)
+    np.testing.assert_allclose(O.gprfitc_lml(X, Y, k, X, 0.2), O.gpr_log_marginal_likelihood(X, Y, k, 0.2), rtol=1e-5)
+    Xs = rng.standard_normal((7, 2))
+    mf, vf = O.gprfitc_predict_f(X, Y, k, X, 0.2, Xs)
+    mg, vg = O.gpr_predict_f(X, Y, k, 0.2, Xs)
+    np.testing.assert_allclose(mf, mg, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(vf, vg, rtol=1e-4, atol=1e-6)
+    W = rng.standard_normal((3, 2))
+    gm, gv = rng.standard_normal((5, 2)), rng.uniform(0.1, 1, (5, 2))
+    m1, v1 = O.mix_latent_gp(W, gm, gv, False, False)
+    m2, v2 = O.mix_latent_gp(W, gm, gv, False, True)
+    np.testing.assert_allclose(np.einsum("npp->np", v2), v1, rtol=1e-12)
+    A = rng.standard_normal((2, 5, 5))
+    gcov = A @ np.transpose(A, (0, 2, 1))
+    _, c1 = O.mix_latent_gp(W, gm, gcov, True, False)
+    _, c2 = O.mix_latent_gp(W, gm, gcov, True, True)
+    np.testing.assert_allclose(np.einsum("npmp->pnm", c2), c1, rtol=1e-12)
+    m3, v3 = O.mix_latent_gp(np.eye(2), gm, gv, False, False)
+    np.testing.assert_allclose(m3, gm), np.testing.assert_allclose(v3, gv)
+
+
+def test_sample_mvn_moments_and_shapes():
+    """tests/gpflow/conditionals/test_conditionals.py::test_sample_mvn: sample mean / covariance converge to the inputs."""
+    rng = np.random.default_rng(8)
+    mean = np.array([[1.0, -2.0]])
+    A = np.array([[1.0, 0.0], [0.8, 0.6]])
+    cov = (A @ A.T)[None]
+    S = 200000
+    s = O.sample_mvn(mean, cov, True, rng.standard_normal((1, 2, S)), jitter=0.0)       # [S, 1, 2]
+    np.testing.assert_allclose(s.mean(0), mean, atol=1e-2)
+    np.testing.assert_allclose(np.cov(s[:, 0, :].T), cov[0], atol=2e-2)
+    d = O.sample_mvn(mean, np.array([[0.25, 4.0]]), False, rng.standard_normal((S, 1, 2)))
+    np.testing.assert_allclose(d.std(0), [[0.5, 2.0]], rtol=2e-2)
