@@ -584,6 +584,39 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = world / (e2e_ms * 1e-3)
 
+    # BASELINE configs[2] names "posterior predict": SGPR.predict_f at Xnew [10000, D] (fused: Kuf/Kuu, two factorisations, the
+    # conditional), timed the same way; serving-style throughput in predicted points per second
+    predict = None
+    if name == "sgpr_c3":
+        from oracle import gp_oracle as _O
+        Xn = arm.gpf.ops.to_device(_O.make_data(3, hp["N"], hp["D"], 1, M=hp["M"], n_new=10000, dtype=hp["dtype"])["Xnew"])
+        m0 = arm.models[0]
+        for _ in range(2):
+            m0.predict_f(Xn)
+        psteps = max(3, steps // 2)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(psteps):
+            mean, var = m0.predict_f(Xn)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / psteps
+        post = m0.posterior()
+        for _ in range(2):
+            post.predict_f(Xn)
+        p0.record()
+        for _ in range(psteps):
+            post.predict_f(Xn)
+        p1.record()
+        torch.cuda.synchronize()
+        cms = p0.elapsed_time(p1) / psteps
+        predict = {"n_new": 10000, "fused_predict_f_ms": pms, "fused_points_per_s": 10000 / (pms * 1e-3),
+                   "cached_posterior_predict_f_ms": cms, "cached_points_per_s": 10000 / (cms * 1e-3),
+                   "note": "fused = SGPR.predict_f (factorisations redone per call, posteriors.py:520-551); cached = "
+                           "model.posterior() once, then posterior.predict_f (PrecomputeCacheType.TENSOR)"}
+        del Xn, mean, var, post
+
     # BASELINE configs[3] (SVGP, 8 latent GPs) on the same GPUs, every sharding mode: the multi-GPU row of the north star
     svgp = None
     if not args.no_svgp and name != "svgp_c4":
@@ -627,8 +660,10 @@ def run_ours(args):
             "share_of_step": prof["tcgen05"]["ms_per_step"] / ms_step,
             "traffic": ncu.get("syrk_i8_dram_bytes_per_launch"),
             "traffic_source": ncu.get("syrk_i8_source"),
-            "dmma_class": {"kernels": "gemm_dmma_kernel (K < 512 trailing updates) + potrf_panel_kernel, mma.sync.m8n8k4.f64",
-                           "achieved_tflops": 2.0 * prof["gemm_dmma_simt"]["issued_macs_per_step"] / dm_s / 1e12 if dm_s > 0 else 0.0,
+            "dmma_class": {"kernels": "potrf_panel_kernel (panel solve + fused K = 128 update) + gemm_dmma_kernel (trailing updates "
+                                      "below the tcgen05 threshold), mma.sync.m8n8k4.f64",
+                           "achieved_tflops": 2.0 * (prof["gemm_dmma_simt"]["issued_macs_per_step"] + prof["panel_solve"]["issued_macs_per_step"])
+                           / (dm_s + pn_s) / 1e12 if dm_s + pn_s > 0 else 0.0,
                            "peak_tflops": dmma_peak, "peak_source": "gpk_peak_probe (DMMA, registers only, all SMs)",
                            "ms_per_step": prof["gemm_dmma_simt"]["ms_per_step"], "panel_ms_per_step": prof["panel_solve"]["ms_per_step"]},
             "whole_factorisation": {"algorithmic_fp64_flops": work["chol_flops"],
@@ -704,6 +739,8 @@ def run_ours(args):
     }
     if grad is not None:
         line["value_and_grad"] = grad
+    if predict is not None:
+        line["posterior_predict"] = predict
     if svgp is not None:
         line["svgp_c4"] = svgp
     emit(line)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "gpk_kdiag": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "gpk_potrf_ws": (c_size_t, [c_int64, c_int64, c_int]),
     "gpk_potrf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpk_potrf_batched_ws": (c_size_t, [c_int64, c_int, c_int]),
     "gpk_potrf_batched": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gpk_trsm_ws": (c_size_t, [c_int64, c_int]),
     "gpk_trsm": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p,
@@ -97,6 +98,7 @@ SIGNATURES = {
     "gpk_prof_read2": (c_int, [_F64, POINTER(c_int64), _F64, c_int]),
     "gpk_peak_probe": (c_int, [_F64, c_void_p]),
     "gpk_potrf_last_slices": (c_int, []),
+    "gpk_warm": (c_int, [c_size_t, c_void_p]),
     "gpk_gpr_lml_ws": (c_size_t, [c_int64, c_int64, c_int]),
     "gpk_gpr_lml": (c_int, [_KN, c_int, _I32, _F64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_double,
                             c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -70,6 +70,10 @@ int trtri_diag_any(const void* L, int64_t n, int64_t ldl, void* dinv, int dtype,
 
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st);
 int peak_probe(double* out_host, cudaStream_t st);
+int lookahead_warm(cudaStream_t st);
+int tf32_reserve(size_t bytes, cudaStream_t st);
+template <typename T>
+int potrf_batched_small_t(T* A, int64_t n, int64_t lda, int64_t stride, int batch, int32_t* info, T* dinv, cudaStream_t st);
 int kaux_impl(const gpk_kaux_desc* d, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2,
               void* K, int64_t ldk, int dtype, cudaStream_t st);
 int kaux_diag_impl(const gpk_kaux_desc* d, const void* X, int64_t N, int64_t ldx, void* out, int dtype, cudaStream_t st);
@@ -126,6 +130,12 @@ int gpk_peak_probe(double* out_host, void* stream) {
 int gpk_prof_read(double* ms, int64_t* launches, int n) { return gpk_prof_read2(ms, launches, nullptr, n); }
 
 int gpk_potrf_last_slices(void) { return potrf_last_slices(); }
+
+int gpk_warm(size_t tf32_scratch_bytes, void* stream) {
+  GPK_TRY(lookahead_warm((cudaStream_t)stream));
+  if (tf32_scratch_bytes) GPK_TRY(tf32_reserve(tf32_scratch_bytes, (cudaStream_t)stream));
+  return 0;
+}
 
 int gpk_kaux(const gpk_kaux_desc* desc, const void* X, int64_t N, int64_t ldx, const void* X2, int64_t N2, int64_t ldx2, void* K,
              int64_t ldk, int dtype, void* stream) {
@@ -191,11 +201,22 @@ int gpk_potrf(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t*
   return potrf_any(A, n, rows, lda, dtype, info, ws, (cudaStream_t)stream);
 }
 
+size_t gpk_potrf_batched_ws(int64_t n, int batch, int dtype) {
+  if (n <= NB) return (size_t)(batch > 0 ? batch : 1) * NB * NB * dtype_size(dtype);  // one inverse slot per matrix
+  return potrf_ws_bytes(n, n, dtype);
+}
+
 int gpk_potrf_batched(void* A, int64_t n, int64_t lda, int64_t stride, int batch, int dtype, int32_t* info, void* ws,
                       void* stream) {
   GPK_DTYPE_OK("potrf_batched");
   GPK_CHECK_ARG(A && ws && n >= 0 && lda >= n && batch >= 0, "potrf_batched: bad arguments");
-  for (int b = 0; b < batch; ++b)  // ws: gpk_potrf_ws(n, n, dtype), reused by every matrix of the batch
+  if (n <= NB) {  // the whole batch in ONE launch: grid over the matrices
+    if (dtype == GPK_F64)
+      return potrf_batched_small_t<double>((double*)A, n, lda, stride, batch, info, (double*)ws, (cudaStream_t)stream);
+    return potrf_batched_small_t<float>((float*)A, n, lda, stride, batch, info, (float*)ws, (cudaStream_t)stream);
+  }
+  // larger matrices: each factorisation already fills the GPU; they run back to back on the stream and share the workspace
+  for (int b = 0; b < batch; ++b)
     GPK_TRY(potrf_any((char*)A + (size_t)b * stride * dtype_size(dtype), n, n, lda, dtype, info ? info + b : nullptr,
                       ws, (cudaStream_t)stream));
   return 0;

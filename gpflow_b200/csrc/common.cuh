@@ -130,7 +130,8 @@ size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype);
 // tcgen05 kind::tf32 (3xTF32) fp32 GEMM, gemm_tf32.cu
 bool gemm_tf32_eligible(int64_t m, int64_t n, int64_t k, const void* A, const void* B, const void* C, int flags);
 int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
-              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int flags, cudaStream_t st);
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int flags, cudaStream_t st, int batch = 1,
+              int64_t a_batch_stride = 0, int64_t c_batch_stride = 0);
 
 template <typename T>
 int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, int64_t ldb, const T* dinv,

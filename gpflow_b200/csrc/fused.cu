@@ -5,6 +5,8 @@
 //   sgpr_elbo : gpflow/models/sgpr.py:181-289 (+ the cache of posteriors.py:520-551)
 //   svgp_elbo : gpflow/models/svgp.py:166-181 -> posteriors.py:827-841 -> conditionals/util.py:84-169
 //               -> kullback_leiblers.py:59-165 -> likelihoods/scalar_continuous.py:139-148
+#include <stdlib.h>
+
 #include "internal.cuh"
 
 namespace gpk {
@@ -334,9 +336,15 @@ int svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const do
   // fmean = A^T q_mu[:, p_begin:p_end]   (util.py:144)
   GPK_TRY(gemm_any(1, 0, B, Pl, M, 1.0, w.A, w.ldb, qmu + (size_t)p_begin * ts, P, 0.0, w.fmu, Pl, dtype, 0, st));
   // fvar_p = fvar0 + sum_m (q_sqrt_p^T A)^2   (util.py:149-164) — LTA is never materialised
+  // fp32, dense q_sqrt: ALL latents in one batched tcgen05 launch (A split into TF32 planes once, one persistent grid
+  // over P x tiles instead of P launches with a 2-wave tail each)
+  static const bool batch_on = []() { const char* e = getenv("GPK_SVGP_BATCHED"); return !(e && e[0] == '0'); }();
+  const bool batched = batch_on && !q_diag && dtype == GPK_F32 && Pl > 1 && M % 256 == 0 &&
+                       gemm_tf32_eligible(M, B, M, nullptr, nullptr, nullptr, 0);
   for (int64_t p = p_begin; p < p_end; ++p) {
     char* fv = (char*)w.fvar + (size_t)(p - p_begin) * B * ts;
     GPK_CUDA_OK(cudaMemcpyAsync(fv, w.v0, (size_t)B * ts, cudaMemcpyDeviceToDevice, st));
+    if (batched) continue;
     if (q_diag) {
       GPK_TRY(colsumsq_impl(w.A, M, B, w.ldb, 1.0, 1, fv, dtype, st, qs + (size_t)p * ts, P));
     } else {
@@ -344,6 +352,9 @@ int svgp_elbo(const gpk_knode* nodes, int n_nodes, const int32_t* dims, const do
                        GPK_GEMM_A_LOWER | GPK_GEMM_COLSUMSQ, st));
     }
   }
+  if (batched)
+    GPK_TRY(gemm_tf32(1, 0, M, B, M, 1.0f, (const float*)(qs + (size_t)p_begin * M * M * ts), M, (const float*)w.A, w.ldb, 0.0f,
+                      (float*)w.fvar, 0, GPK_GEMM_A_LOWER | GPK_GEMM_COLSUMSQ, st, (int)Pl, M * M, B));
   // sum of variational expectations (scalar_continuous.py:139-148); Yc column range [p_begin, p_end)
   GPK_TRY(varexp_impl(w.fmu, w.fvar, (const char*)Yc + (size_t)p_begin * ts, B, Pl, P, 1, B, noise, 1.0, 1,
                       w.scal + 0, dtype, st));

@@ -82,9 +82,10 @@ slice_rows_kernel(const double* __restrict__ P, int64_t ld, int64_t row0, int64_
       uint32_t w = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const double d = rint(v[q]);                 // |d| <= 64
+        int di;
+        const double d = tc_round_digit(v[q], di);   // |d| <= 64
         v[q] = (v[q] - d) * 128.0;                   // exact: remainder, rescaled for the next digit
-        w |= (uint32_t)((int)d & 0xff) << (8 * q);
+        w |= (uint32_t)(di & 0xff) << (8 * q);
       }
       *reinterpret_cast<uint32_t*>(tb + (size_t)s * TC_ATILE) = w;
     }
@@ -342,7 +343,7 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
           uint32_t v[32];
           tc_ld32(lane_addr + (uint32_t)(g * TC_BN + half * 32), v);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fma((double)(int)v[c], w, acc[c]);
+          for (int c = 0; c < 32; ++c) acc[c] = fma(tc_int_to_double((int)v[c]), w, acc[c]);
           w *= 0.0078125;  // 2^-7
         }
         if (half == 1) {  // accumulators drained: the MMA warp may start the next tile

@@ -52,7 +52,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 template <int RB>
 __global__ void __launch_bounds__(256)
 split_tiles_kernel(const float* __restrict__ src, int64_t R, int64_t K, int64_t ld, int trans, int tri,
-                   float* __restrict__ tiles, int64_t KBn) {
+                   float* __restrict__ tiles, int64_t KBn, int64_t rows_per_batch, int64_t batch_stride) {
+  // rows_per_batch > 0: the logical [R, K] operand is a vertical stack of R / rows_per_batch matrices stored
+  // batch_stride elements apart (the P lower-triangular q_sqrt_p of the SVGP conditional): row r = (batch, r % rows)
   // one thread = one 16-byte k-chunk (4 consecutive k) of one row
   const int64_t Rpad = (R + RB - 1) / RB * RB;
   const int64_t nchunk = KBn * 4;  // k-chunks per row
@@ -67,8 +69,10 @@ split_tiles_kernel(const float* __restrict__ src, int64_t R, int64_t K, int64_t 
     const int64_t k = kc * 4 + q;
     float x = 0.f;
     if (r < R && k < K) {
-      const int64_t srow = trans ? k : r, scol = trans ? r : k;
-      if (!(tri && scol > srow)) x = src[srow * ld + scol];
+      const int64_t rl = rows_per_batch > 0 ? r % rows_per_batch : r;
+      const float* sb = rows_per_batch > 0 ? src + (r / rows_per_batch) * batch_stride : src;
+      const int64_t srow = trans ? k : rl, scol = trans ? rl : k;
+      if (!(tri && scol > srow)) x = sb[srow * ld + scol];
     }
     v[q] = x;
   }
@@ -148,7 +152,8 @@ constexpr int TF_THREADS = 320;                 // warp 0 producer, warp 1 MMA, 
 // upper triangular (k >= row, e.g. tril(q_sqrt)^T): the all-zero part of the K range is skipped (whole runs), which
 // halves the P batched products  tril(q_sqrt_p)^T A  of the SVGP conditional (conditionals/util.py:151-157).
 __device__ __forceinline__ void tf_krange(int tri, int64_t tm_first, int64_t tm_last, int KB, int nsplit, int ks, int& kb0,
-                                          int& kb1) {  // common range of the row tiles tm_first..tm_last of one unit
+                                          int& kb1, int tpb = 0) {  // common range of the row tiles tm_first..tm_last of one unit
+  if (tpb > 0) { tm_first %= tpb; tm_last %= tpb; }  // stacked triangular operands: position inside the own matrix
   int lo = 0, hi = KB;
   if (tri == 2) lo = (int)((tm_first * TF_BM / TF_KS) / TF_SPP * TF_SPP);
   if (tri == 1) { const int64_t e = ((tm_last + 1) * TF_BM + TF_KS - 1) / TF_KS; if (e < hi) hi = (int)e; }
@@ -164,7 +169,10 @@ __device__ __forceinline__ void tf_krange(int tri, int64_t tm_first, int64_t tm_
 template <int CL>
 __global__ void __launch_bounds__(TF_THREADS, 1)
 gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Btiles, float* C, int64_t ldc, int64_t m,
-                 int64_t n, int KB, int nsplit, float alpha, float beta, int flags, int tri, int* err) {
+                 int64_t n, int KB, int nsplit, float alpha, float beta, int flags, int tri, int* err, int tpb,
+                 int64_t c_batch_stride) {
+  // tpb > 0: op(A) is a vertical stack of matrices of tpb row tiles each (batched tril(q_sqrt_p)^T A); the fused column
+  // sums of squares of matrix b go to C + b * c_batch_stride
   extern __shared__ __align__(1024) uint8_t tf_smem[];
   uint8_t* epi = tf_smem + TF_STAGES * TF_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 2 * TF_EPI_BYTES);  // full[4], empty[4], tfull[2], tempty[2]
@@ -194,7 +202,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     uint32_t st = 0, ph = 0;
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1, tpb);
       const char* a_src = reinterpret_cast<const char*>(Atiles) + (size_t)w.tm_load() * KB * 2 * TF_APLANE;
       const char* b_src = reinterpret_cast<const char*>(Btiles) + (size_t)w.tn * KB * 2 * TF_BPLANE;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -225,7 +233,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1, tpb);
       for (int kr = kb0; kr < kb1; kr += TF_SPP) {
         mbar_wait(tempty0 + 8 * buf, (buf ? tph1 : tph0) ^ 1, err, 202);
         tc_fence_after();
@@ -267,7 +275,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
     uint32_t buf = 0, tph0 = 0, tph1 = 0;
     while (w.next()) {
       int kb0, kb1;
-      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1);
+      tf_krange(tri, w.tm0, w.tm0 + CL - 1, KB, nsplit, w.ks, kb0, kb1, tpb);
       float acc[128];
 #pragma unroll
       for (int c = 0; c < 128; ++c) acc[c] = 0.f;
@@ -303,7 +311,7 @@ gemm_tf32_kernel(const float* __restrict__ Atiles, const float* __restrict__ Bti
               const float x = row0 + r < m ? tile[r * 33 + lane] : 0.f;
               s = fmaf(x, x, s);
             }
-            if (col < n) atomicAdd(C + col, s);
+            if (col < n) atomicAdd(C + (tpb > 0 ? (w.tm / tpb) * c_batch_stride : 0) + col, s);
           } else if (col < n) {
             float* cbase = C + row0 * ldc + col;
             if (nsplit > 1) {
@@ -372,6 +380,13 @@ static void* tf_scratch(size_t bytes, cudaStream_t st, int* rc) {
   return b.p;
 }
 
+// eager reservation of the plane scratch for this (device, stream) (gpk_warm)
+int tf32_reserve(size_t bytes, cudaStream_t st) {
+  int rc = 0;
+  tf_scratch(bytes, st, &rc);
+  return rc;
+}
+
 bool tf32_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPK_FP32_ENGINE"); v = (e && strcmp(e, "simt") == 0) ? 0 : 1; }
@@ -395,7 +410,16 @@ bool gemm_tf32_eligible(int64_t m, int64_t n, int64_t k, const void* A, const vo
 }
 
 int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
-              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int flags, cudaStream_t st) {
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int flags, cudaStream_t st, int batch,
+              int64_t a_batch_stride, int64_t c_batch_stride) {
+  // batch > 1 (COLSUMSQ only): op(A) = [op(A_0); ...; op(A_{batch-1})], A_b = A + b * a_batch_stride, all against the same
+  // B; column sums of squares of block b accumulate into C + b * c_batch_stride.  ONE launch (B split once, one persistent
+  // grid over batch * tiles) instead of `batch` launches with a 2-wave tail each.
+  const int64_t m_per = m;
+  if (batch > 1) {
+    GPK_CHECK_ARG((flags & GPK_GEMM_COLSUMSQ) && m % (2 * TF_BM) == 0, "gemm_tf32: batched form needs COLSUMSQ and m %% 256 == 0");
+    m *= batch;
+  }
   const int64_t KB = (k + TF_KS - 1) / TF_KS;
   const int64_t mpad = (m + TF_BM - 1) / TF_BM * TF_BM, npad = (n + TF_BN - 1) / TF_BN * TF_BN;
   const size_t a_bytes = (size_t)mpad * KB * TF_KS * 4 * 2, b_bytes = (size_t)npad * KB * TF_KS * 4 * 2;
@@ -410,11 +434,12 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
     // op(A) is [m, k]: stored [m,k] (transa = 0, k contiguous) or [k,m] (transa = 1)
     const int64_t tot_a = mpad * KB * 4;
     split_tiles_kernel<TF_BM><<<(unsigned)((tot_a + 255) / 256), 256, 0, st>>>(A, m, k, lda, transa ? 1 : 0,
-                                                                               (flags & GPK_GEMM_A_LOWER) ? 1 : 0, At, KB);
+                                                                               (flags & GPK_GEMM_A_LOWER) ? 1 : 0, At, KB,
+                                                                               batch > 1 ? m_per : 0, a_batch_stride);
     GPK_LAUNCH_OK();
     // op(B)^T is [n, k]: stored [n,k] (transb = 1) or [k,n] (transb = 0 -> read transposed)
     const int64_t tot_b = npad * KB * 4;
-    split_tiles_kernel<TF_BN><<<(unsigned)((tot_b + 255) / 256), 256, 0, st>>>(B, n, k, ldb, transb ? 0 : 1, 0, Bt, KB);
+    split_tiles_kernel<TF_BN><<<(unsigned)((tot_b + 255) / 256), 256, 0, st>>>(B, n, k, ldb, transb ? 0 : 1, 0, Bt, KB, 0, 0);
     GPK_LAUNCH_OK();
   }
   const int lower = (flags & GPK_GEMM_LOWER_ONLY) ? 1 : 0;
@@ -445,7 +470,7 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   }));
   int grid = (int)std::min<int64_t>(sms / cl * cl, nunits * cl * nsplit);
   const int tri = (flags & GPK_GEMM_A_LOWER) ? (transa ? 2 : 1) : 0;
-  ProfScope ps(PROF_TC, st, 3.0 * (double)m * (double)n * (double)k * (tri ? 0.5 : 1.0));  // tf32 MACs issued (3xTF32)
+  ProfScope ps(PROF_TC, st, 3.0 * (double)m * (double)n * (double)k * (tri ? 0.5 : 1.0));  // (m already includes the batch)  // tf32 MACs issued (3xTF32)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TF_THREADS);
@@ -461,10 +486,13 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   const float* Atc = At;
   const float* Btc = Bt;
   const int KBi = (int)KB;
+  const int tpb = batch > 1 ? (int)(m_per / TF_BM) : 0;
   if (cl == 2)
-    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<2>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err));
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<2>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err,
+                                   tpb, c_batch_stride));
   else
-    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<1>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err));
+    GPK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<1>, Atc, Btc, C, ldc, m, n, KBi, nsplit, alpha, beta, flags, tri, err,
+                                   tpb, c_batch_stride));
   count_launch();
   return 0;
 }

@@ -320,7 +320,12 @@ __device__ __forceinline__ void write_dinv64(const T* S, T* __restrict__ dinv) {
 template <typename T, bool SLIM>
 __global__ void __launch_bounds__(256, 1)
 potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base,
-                  long long* dbg, int* wait_flag, int wait_target) {
+                  long long* dbg, int* wait_flag, int wait_target, int64_t batch_stride) {
+  // grid > 1: a BATCH of independent blocks (gpk_potrf_batched, n <= 128), block b at A + b * batch_stride with its own
+  // inverse slot and info word
+  A += (int64_t)blockIdx.x * batch_stride;
+  dinv += (size_t)blockIdx.x * NB * NB;
+  if (info) info += blockIdx.x;
   extern __shared__ __align__(16) unsigned char leaf_smem[];
   T* S = reinterpret_cast<T*>(leaf_smem);  // [128][129]
   T* ldiag = S + NB * LS;                  // [128] diagonal of L
@@ -600,9 +605,10 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
         uint32_t wd[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const double d = rint(v[u]);
+          int di;
+          const double d = tc_round_digit(v[u], di);
           v[u] = (v[u] - d) * 128.0;
-          wd[u >> 2] |= (uint32_t)((int)d & 0xff) << (8 * (u & 3));
+          wd[u >> 2] |= (uint32_t)(di & 0xff) << (8 * (u & 3));
         }
         *reinterpret_cast<uint4*>(tb + (size_t)s2 * TC_ATILE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
       }
@@ -787,6 +793,14 @@ static int lookahead_init(LookAhead& la, int* flag, cudaStream_t st) {
 }
 
 // C = A[col0 + n1 :, col0 + n1 : col0 + n] -= P P[0 : n - n1]^T with P = the finished columns [col0, col0 + K) below
+// eager creation of the (device, stream) look-ahead resources (gpk_warm): the first factorisation on a stream otherwise
+// creates one side stream and three events lazily
+int lookahead_warm(cudaStream_t st) {
+  LookAhead la;
+  int dummy = 0;
+  return lookahead_init(la, &dummy, st);
+}
+
 template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, int64_t col0,
                            LookAhead& la, cudaStream_t st) {
@@ -841,9 +855,9 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   {
     ProfScope ps(PROF_LEAF, ls);
     if (la.slim)
-      potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+      potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0);
     else
-      potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt);
+      potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0);
     GPK_LAUNCH_OK();
   }
   if (rows <= n) {
@@ -879,7 +893,8 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
     la.pending = true;
     {
-      ProfScope ps(PROF_PANEL, st);
+      // work: MACs of the solve (half of rows x 128 x 128: triangular) + the fused K = 128 update
+      ProfScope ps(PROF_PANEL, st, (double)(rows - n) * n * (0.5 * n + fuse_cols));
       const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
       potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(true), st>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
                                                                      (int)n, (const double*)dblk, em, fu);
@@ -890,7 +905,7 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   }
   if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
   if (la.slim) {
-    ProfScope ps(PROF_PANEL, ls);
+    ProfScope ps(PROF_PANEL, ls, (double)(rows - n) * n * 0.5 * n);
     const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
     potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(), ls>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
                                                                (int)n, (const double*)dblk, em, fu);
@@ -971,6 +986,22 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   return 0;
 }
 
+// Batch of small factorisations (n <= 128): ONE launch, one CTA per matrix (multi-output Kuu stacks [L, M, M]).
+template <typename T>
+int potrf_batched_small_t(T* A, int64_t n, int64_t lda, int64_t stride, int batch, int32_t* info, T* dinv, cudaStream_t st) {
+  if (n <= 0 || batch <= 0) return 0;
+  GPK_CHECK_ARG(n <= NB, "potrf_batched_small: n = %lld > %d", (long long)n, NB);
+  GPK_TRY(leaf_attr<T>());
+  if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, (size_t)batch * sizeof(int32_t), st));
+  ProfScope ps(PROF_LEAF, st);
+  potrf_leaf_kernel<T, false><<<(unsigned)batch, 256, leaf_smem_bytes<T>(), st>>>(A, lda, (int)n, dinv, info, 0, nullptr, nullptr,
+                                                                                  0, stride);
+  GPK_LAUNCH_OK();
+  return 0;
+}
+template int potrf_batched_small_t<float>(float*, int64_t, int64_t, int64_t, int, int32_t*, float*, cudaStream_t);
+template int potrf_batched_small_t<double>(double*, int64_t, int64_t, int64_t, int, int32_t*, double*, cudaStream_t);
+
 template <typename T>
 int trtri_diag_t(const T* L, int64_t n, int64_t ldl, T* dinv, cudaStream_t st) {
   if (n <= 0) return 0;
@@ -1013,7 +1044,7 @@ int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, in
 // phase timing of one leaf launch (clock64 at phase boundaries), for tuning
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
   GPK_TRY(leaf_attr<double>());
-  potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0);
+  potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0, 0);
   GPK_LAUNCH_OK();
   return 0;
 }

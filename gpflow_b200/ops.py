@@ -181,6 +181,22 @@ def potrf(A, n: Optional[int] = None, *, check_info: bool = True):
     return A, ws
 
 
+def potrf_batched(A, *, check_info: bool = True):
+    """In-place lower Cholesky of a batch A [L, n, n] (multi-output Kuu stacks); n <= 128 runs as ONE launch."""
+    Lb, n = A.shape[0], A.shape[-1]
+    lib = _lib.load()
+    dc = dtype_code(A)
+    ws = scratch_bytes(lib.gpk_potrf_batched_ws(n, Lb, dc))
+    info = torch().empty((Lb,), dtype=torch().int32, device=A.device)
+    check(lib.gpk_potrf_batched(_p(A), n, A.stride(-2), A.stride(0), Lb, dc, _p(info), _p(ws), _stream()), "gpk_potrf_batched")
+    if check_info:
+        bad = info.cpu().numpy()
+        if bad.any():
+            b = int(bad.nonzero()[0][0])
+            raise NonPositiveDefiniteError(f"Cholesky decomposition was not successful (matrix {b}, pivot {int(bad[b])} <= 0)")
+    return A, ws
+
+
 def cholesky(K):
     """tf.linalg.cholesky semantics: new tensor, strict upper triangle zero."""
     L = empty(K.shape, like=K)
@@ -307,6 +323,11 @@ def add_diag_(A, scalar: float = 0.0, vec=None):
 
 
 def fill(A, value: float):
+    if A.dim() > 2:
+        if not A.is_contiguous():
+            raise ValueError("fill: tensors with more than two dimensions must be contiguous")
+        fill(A.view(-1, A.shape[-1]), value)
+        return A
     if A.dim() <= 1:
         m, n, ld = 1, A.numel(), A.numel()
     else:

@@ -12,8 +12,11 @@
  * Conventions
  *  - All matrices are ROW-MAJOR (C order, like NumPy/TF); `ld*` = elements between rows.
  *  - All data pointers are DEVICE pointers (e.g. torch.Tensor.data_ptr()) unless named `host`.
- *    The caller owns all memory; workspaces come from the matching `*_ws` size query; no hidden
- *    cudaMalloc on the hot path.
+ *    The caller owns all memory; workspaces come from the matching `*_ws` size query.  Two resources
+ *    are library-owned, keyed by (device, stream), created on first use and never on the steady-state
+ *    path: the side stream + 3 events of the Cholesky look-ahead, and the grow-only TF32 plane scratch
+ *    of the fp32 tcgen05 GEMM (gpk_gemm has no workspace argument in the reference-shaped ABI).
+ *    gpk_warm() creates / reserves them eagerly.
  *  - `dtype`: GPK_F32 or GPK_F64; every array of one call has that dtype (gpflow/base.py:299-311).
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
  *  - Return: 0 = OK; <0 = argument / launch error (text via gpk_last_error()); potrf reports a
@@ -109,7 +112,11 @@ GPK_API size_t gpk_potrf_ws(int64_t n, int64_t rows, int dtype);
 GPK_API int gpk_potrf(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws,
               void* stream);
 
-/* Batched variant: `batch` matrices `stride` elements apart (multi-output [L,M,M]). */
+/* Batched variant: `batch` matrices `stride` elements apart (multi-output Kuu stacks [L, M, M],
+ * gpflow/covariances/multioutput/kuus.py:62-122).  n <= 128: the whole batch is ONE launch (one CTA per matrix) and the
+ * workspace receives one 128x128 inverse slot per matrix; larger n: the factorisations run back to back on the stream.
+ * ws: gpk_potrf_batched_ws(n, batch, dtype) bytes.  info: `batch` device words. */
+GPK_API size_t gpk_potrf_batched_ws(int64_t n, int batch, int dtype);
 GPK_API int gpk_potrf_batched(void* A, int64_t n, int64_t lda, int64_t stride, int batch, int dtype,
                       int32_t* info, void* ws, void* stream);
 
@@ -317,6 +324,9 @@ GPK_API int gpk_peak_probe(double* out_host, void* stream);
 /* Digit planes S used by the tcgen05 trailing updates of the most recent fp64 factorisation on this process (chosen from
  * the conditioning hint of the caller: 7, 8, or 0 = the updates ran on fp64 DMMA). */
 GPK_API int gpk_potrf_last_slices(void);
+/* Eager creation of the library-owned per-(device, stream) resources (see "Conventions"): the look-ahead side stream and
+ * events, and `tf32_scratch_bytes` of TF32 plane scratch (0 = skip; 2 * 4 * (m + n) * k bytes cover an m x n x k product). */
+GPK_API int gpk_warm(size_t tf32_scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,7 +97,20 @@ def full():
     json.dump(res, open(os.path.join(HERE, "golden_full.json"), "w"), indent=1)
 
 
+def c3_predict_full():
+    """BASELINE configs[2] "posterior predict" at full size: SGPR posterior mean / variance at Xnew [10000, 16]
+    (gpflow/posteriors.py:479-551).  Stored: the first 256 rows and the sums over all 10000 (size-independent checksum)."""
+    d = O.make_data(3, 100000, 16, 1, M=1024, n_new=10000)
+    m, v = O.sgpr_predict_f(d["X"], d["Y"], kernels_for(3, 16), d["Z"], 0.1, d["Xnew"], jitter=1e-4)
+    np.savez(os.path.join(HERE, "golden_c3_predict.npz"), mean=m[:256], var=v[:256], mean_sum=m.sum(), var_sum=v.sum(),
+             mean_abs_sum=np.abs(m).sum())
+    print("c3 predict", m[:3, 0], v[:3, 0], m.sum(), v.sum())
+
+
 if __name__ == "__main__":
+    if "--c3-predict" in sys.argv:
+        c3_predict_full()
+        sys.exit(0)
     small()
     if "--full" in sys.argv:
         full()

@@ -272,3 +272,28 @@ def test_kbuild_fast_path_modes(cuda_device, name, dtype):
             lchk[5, 4] = lref[5, 4] = 0.0
         assert_allclose(lchk[il], lref[il], **t)
         assert np.all(to_np(low)[:64, 64:] == -3.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 37, 128, 300])
+def test_potrf_batched_matches_lapack(cuda_device, dtype, n):
+    """gpk_potrf_batched: a stack [L, n, n] (multi-output Kuu, covariances/multioutput/kuus.py:62-122); n <= 128 is one
+    launch with one CTA per matrix, larger n runs the factorisations back to back."""
+    rng = np.random.default_rng(n)
+    Lb = 5
+    mats = []
+    for _ in range(Lb):
+        B = rng.standard_normal((n, n + 3))
+        mats.append(B @ B.T / n + 0.5 * np.eye(n))
+    A = np.stack(mats).astype(dtype)
+    with gpf.config.as_context(gpf.config.Config(float=dtype)):
+        Ad = ops.to_device(A.copy())
+        ops.potrf_batched(Ad)
+    got = np.tril(Ad.cpu().numpy().astype(np.float64))
+    ref = np.stack([np.linalg.cholesky(m) for m in A.astype(np.float64)])
+    assert_allclose(got, ref, rtol=0, atol=2e-11 if dtype == np.float64 else 3e-4)
+    bad = A.copy()
+    bad[3, n - 1, n - 1] = -1.0
+    with gpf.config.as_context(gpf.config.Config(float=dtype)):
+        with pytest.raises(ops.NonPositiveDefiniteError):
+            ops.potrf_batched(ops.to_device(bad))

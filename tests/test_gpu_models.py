@@ -420,6 +420,25 @@ def test_c3_full_size_sgpr_elbo_golden(cuda_device):
         assert_allclose(float(m.elbo()), gold, rtol=1e-8)
 
 
+def test_c3_full_size_sgpr_predict_golden(cuda_device):
+    """BASELINE config 3 "posterior predict" at full size: SGPR.predict_f at Xnew [10000, 16] (N = 100000, M = 1024) against
+    the fp64 oracle fixture (tests/golden/golden_c3_predict.npz: first 256 rows + sums over all rows); fp32 within 1e-3 of
+    the prior variance, fp64 within 1e-6.  Reference: gpflow/posteriors.py:479-551."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_c3_predict.npz"))
+    d = O.make_data(3, 100000, 16, 1, M=1024, n_new=10000)
+    for dt, tol in ((np.float32, 1e-3), (np.float64, 1e-6)):
+        with gpf.config.as_context(gpf.config.Config(float=dt, jitter=1e-4)):
+            m = gpf.models.SGPR((d["X"], d["Y"]), product_kernel(3, 16), d["Z"], noise_variance=0.1)
+            mean, var = m.predict_f(d["Xnew"])
+        mean, var = mean.cpu().numpy().astype(np.float64), var.cpu().numpy().astype(np.float64)
+        assert mean.shape == (10000, 1) and var.shape == (10000, 1)
+        assert_allclose(mean[:256], g["mean"], rtol=tol, atol=tol)
+        assert_allclose(var[:256], g["var"], rtol=tol, atol=tol)
+        assert_allclose(mean.sum(), float(g["mean_sum"]), atol=tol * float(g["mean_abs_sum"]))
+        assert_allclose(var.sum(), float(g["var_sum"]), rtol=tol)
+
+
 def test_c4_full_size_svgp_elbo_golden(cuda_device):
     """BASELINE config 4 at full size (B=4096, M=2048, P=8, D=16, num_data=1e6), first minibatch."""
     gold = _gold_full()["c4_elbo_N1e6_B4096_M2048_P8_D16_f64_jitter1e-4_batch0"]

@@ -41,6 +41,10 @@ CASES = {
 def test_materialised_kernels_match_oracle(cuda_device, name, dtype):
     kp, ko = CASES[name][0](), CASES[name][1]()
     tol = dict(rtol=1e-11, atol=1e-11) if dtype == np.float64 else dict(rtol=2e-4, atol=2e-5)
+    if name.startswith("arccos") and dtype == np.float64:
+        # theta = acos(c) has derivative 1 / sqrt(1 - c^2): nearly parallel inputs turn 1e-16 in c into 1e-8 in theta
+        # (the reference's own 1e-15 jitter, misc.py:185, exists for this)
+        tol = dict(rtol=1e-7, atol=2e-8)
     with gpf.config.as_context(gpf.config.Config(float=dtype)):
         Kxx, Kx2, kd = kp(X), kp(X, X2), kp(X, full_cov=False)
     np.testing.assert_allclose(Kxx.cpu().numpy(), ko(X), **tol)
