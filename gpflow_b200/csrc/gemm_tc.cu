@@ -29,7 +29,8 @@
 
 namespace gpk {
 
-constexpr int TC_STAGES = 4;
+constexpr int TC_SMEM_BUDGET = 220 * 1024;  // pipeline stages: as many as fit (S planes of A and B per stage, tightly packed)
+__host__ __device__ constexpr int tc_stages(int S) { return TC_SMEM_BUDGET / (S * (TC_ATILE + TC_BTILE)) > 6 ? 6 : TC_SMEM_BUDGET / (S * (TC_ATILE + TC_BTILE)); }
 constexpr int TC_TMEM_COLS = 512;
 
 // ------------------------------------------------------------------------------------------------
@@ -159,7 +160,9 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
   int* err = pl.err;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
-  uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE);
+  constexpr int TC_STAGES = tc_stages(S);   // S = 7: 5 stages of 42 KB, S = 8: 4 of 48 KB, S = 6: 6 of 36 KB
+  constexpr uint32_t stage_stride = (uint32_t)S * (TC_ATILE + TC_BTILE);
+  uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)stage_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bar_area);  // full[4], empty[4], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,8 +206,8 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
         if (elect_one()) {
           const uint32_t fb = full0 + 8 * st;
           mbar_expect_tx(fb, stage_bytes);
-          const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
-          const uint32_t sb = sa + TC_MAXS * TC_ATILE;
+          const uint32_t sa = smem_u32(tc_smem + (size_t)st * stage_stride);
+          const uint32_t sb = sa + S * TC_ATILE;
           if (CL == 1) {
             bulk_g2s(sa, a_src + (size_t)kb * S * TC_ATILE, (uint32_t)S * TC_ATILE, fb);
           } else {
@@ -234,9 +237,9 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(full0 + 8 * st, ph, err, 103);
         tc_fence_after();
-        const uint32_t sa = smem_u32(tc_smem + (size_t)st * TC_MAXS * (TC_ATILE + TC_BTILE));
+        const uint32_t sa = smem_u32(tc_smem + (size_t)st * stage_stride);
         const uint64_t ad0 = desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
-        const uint64_t bd0 = ad0 + ((TC_MAXS * TC_ATILE) >> 4);
+        const uint64_t bd0 = ad0 + ((S * TC_ATILE) >> 4);
         if (elect_one()) {
           if (TS) {
             // A digit planes -> TMEM (columns S*64 .. S*64 + 8S): every A plane is then read from shared
@@ -487,7 +490,7 @@ int syrk_tc_planes(double* C, int64_t ldc, int64_t m, int64_t n, const TcPlanes&
                 "syrk_tc: unsupported shape m=%lld n=%lld K=%lld r0=%lld k0=%lld", (long long)m, (long long)n, (long long)K,
                 (long long)r0, (long long)k0);
   const int64_t rb0 = r0 / TC_BM, kb0 = k0 / TC_KB;
-  const size_t smem = TC_STAGES * (size_t)TC_MAXS * (TC_ATILE + TC_BTILE) + 256;
+  const size_t smem = tc_stages(S) * (size_t)S * (TC_ATILE + TC_BTILE) + 256;
   // Both operands from shared memory with the digit products of one A plane CONCATENATED along N (one MMA of N up to 256
   // instead of up to four of N = 64): scripts/mb_mma.cu measures 52.9 cycles per N = 64 SS MMA against a floor of 32,
   // but 128.0 per N = 256 MMA (= the floor), and the tcgen05.cp of the TS form costs 137 cycles per k-step on top.

@@ -475,9 +475,11 @@ struct PanelEmit {
   int64_t row_g0;     // global row index of B's first row
   int64_t col_g0;     // global column index of the block
 };
+constexpr int PCR = 16;  // rows per CRITICAL CTA of the fused panel (see the row mapping in the kernel)
 struct PanelFuse {
   double* C;          // nullptr: off.  C[rows, uc] (same rows as B), leading dimension ldb
   int uc;             // columns of the update (<= 128)
+  int ncrit;          // CTAs (PCR rows each) that cover the first uc rows = X_top = the next diagonal block
   int* flag;          // [1]: 32x32 units of the next diagonal block done, [2]: X_top CTAs finished
   int64_t mu, nu;     // shape of the whole update (rows, uc) for diag_units_tile
 };
@@ -491,7 +493,14 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   double* Di = Ai + 64 * PLW;                          // [64][PLW]  D^-1
   double* Cs = Di + 64 * PLW;                          // [64][PLW]  C = L[64:128, 0:64]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int64_t r0 = (int64_t)blockIdx.x * PR;
+  // Row mapping.  Plain: 64 rows per CTA.  Fused: the first fu.ncrit CTAs take PCR = 16 rows each of the CRITICAL rows (the
+  // rows of the next diagonal block: X_top, and the block the next leaf is waiting for) -- two active warps per SM instead of
+  // eight sharing the DMMA pipe, so their solve + update finish in a fraction of the time; the rest 64 rows each below them.
+  const int ncrit = fu.C ? fu.ncrit : 0;
+  const bool critical = (int)blockIdx.x < ncrit;
+  const int nrows_cta = critical ? PCR : PR;
+  const int64_t r0 = critical ? (int64_t)blockIdx.x * PCR : (int64_t)ncrit * PCR + (int64_t)(blockIdx.x - ncrit) * PR;
+  const bool wact = w * 8 < nrows_cta;  // warps beyond the CTA's rows only help with the cooperative loads / emission
   for (int e = tid; e < 4096; e += 256) {
     const int i = e >> 6, j = e & 63;
     Ai[i * PLW + j] = dinv64[e];
@@ -499,18 +508,21 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     Cs[i * PLW + j] = (64 + i < nb) ? Lblk[(int64_t)(64 + i) * ldl + j] : 0.0;
   }
   double* Bw = Bs + (w * 8) * PLB;  // this warp's 8 rows
+  if (wact) {
 #pragma unroll
-  for (int rr = 0; rr < 8; ++rr) {
-    const int64_t row = r0 + w * 8 + rr;
+    for (int rr = 0; rr < 8; ++rr) {
+      const int64_t row = r0 + w * 8 + rr;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c = lane + 32 * cc;
-      Bw[rr * PLB + c] = (row < rows && c < nb) ? B[row * ldb + c] : 0.0;
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = lane + 32 * cc;
+        Bw[rr * PLB + c] = (row < rows && c < nb) ? B[row * ldb + c] : 0.0;
+      }
     }
   }
   __syncthreads();
 
   double acc[8][2], af[16];
+  if (wact) {
   // ---- phase 1: X1 = B1 A^-T;  (A^-T)[k][n] = Ai[n][k], zero for k > n
 #pragma unroll
   for (int ks = 0; ks < 16; ++ks) af[ks] = Bw[g * PLB + ks * 4 + q];
@@ -569,9 +581,10 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
       }
     }
   }
+  }  // wact
   // ---- fused K = nb update of the next block column: X_top published first (everybody needs it)
   if (fu.C) {
-    const int ntop = (fu.uc + PR - 1) / PR;  // CTAs that own rows of X_top
+    const int ntop = ncrit;                  // CTAs that own rows of X_top
     __syncthreads();                         // all warps' rows are in global memory
     if ((int)blockIdx.x < ntop && tid == 0) {
       __threadfence();
@@ -587,8 +600,8 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     if (!fu.C) __syncthreads();  // (the fused path has passed a barrier already) all warps' rows are in Bs
     const int S = em.pl.S;
 #pragma unroll 1
-    for (int e = tid; e < PR * 8; e += 256) {
-      const int rl = e & (PR - 1), ch = e >> 6;  // local row, 16-column chunk
+    for (int e = tid; e < nrows_cta * 8; e += 256) {
+      const int rl = e % nrows_cta, ch = e / nrows_cta;  // local row, 16-column chunk
       const int64_t row = r0 + rl, grow = em.row_g0 + row;
       if (row >= rows || grow >= em.pl.n_sq) continue;
       const double inv = 1.0 / em.pl.rowscale[grow];  // exact: a power of two
@@ -616,12 +629,11 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   };
   // CTAs that hold rows of the next diagonal block update and publish them first (the next leaf is waiting for them) and
   // emit their planes afterwards; everybody else emits while waiting for X_top
-  const bool critical = fu.C && r0 < (int64_t)NB;
   if (!critical) emit_planes();
   if (!fu.C) return;
   // ---- C[own rows, 0:uc] -= X[own rows, 0:nb] X_top[0:uc, 0:nb]^T
   {
-    const int ntop = (fu.uc + PR - 1) / PR;
+    const int ntop = ncrit;
     double* Xt = Ai;  // [128][PLB] staged X_top: reuses the operand area (everybody passed the barrier above)
     if (tid == 0) {
       unsigned spins = 0;
@@ -648,24 +660,27 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     }
     // accumulators = this warp's 8 rows of C (DMMA C-fragment layout: row g, columns 8 cb + 2q, +1)
     const int64_t crow = r0 + w * 8 + g;
+    const bool rok = wact && crow < rows;
     double cacc[16][2];
 #pragma unroll
     for (int cb = 0; cb < 16; ++cb) {
       const int c = cb * 8 + 2 * q;
-      cacc[cb][0] = (crow < rows && c < fu.uc) ? fu.C[crow * ldb + c] : 0.0;
-      cacc[cb][1] = (crow < rows && c + 1 < fu.uc) ? fu.C[crow * ldb + c + 1] : 0.0;
+      cacc[cb][0] = (rok && c < fu.uc) ? fu.C[crow * ldb + c] : 0.0;
+      cacc[cb][1] = (rok && c + 1 < fu.uc) ? fu.C[crow * ldb + c + 1] : 0.0;
     }
     __syncthreads();
+    if (wact) {
 #pragma unroll 1
-    for (int kh = 0; kh < 2; ++kh) {  // two halves of k keep the A fragments at 16 registers
+      for (int kh = 0; kh < 2; ++kh) {  // two halves of k keep the A fragments at 16 registers
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) af[ks] = -Bw[g * PLB + kh * 64 + ks * 4 + q];
+        for (int ks = 0; ks < 16; ++ks) af[ks] = -Bw[g * PLB + kh * 64 + ks * 4 + q];
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks)
+        for (int ks = 0; ks < 16; ++ks)
 #pragma unroll
-        for (int cb = 0; cb < 16; ++cb) dmma884p(cacc[cb], af[ks], Xt[(cb * 8 + g) * PLB + kh * 64 + ks * 4 + q]);
+          for (int cb = 0; cb < 16; ++cb) dmma884p(cacc[cb], af[ks], Xt[(cb * 8 + g) * PLB + kh * 64 + ks * 4 + q]);
+      }
     }
-    if (crow < rows) {
+    if (rok) {
 #pragma unroll
       for (int cb = 0; cb < 16; ++cb) {
         const int c = cb * 8 + 2 * q;
@@ -673,13 +688,12 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
         if (c + 1 < fu.uc) fu.C[crow * ldb + c + 1] = cacc[cb][1];
       }
     }
-    // look-ahead: rows of the next diagonal block are complete
-    const int u = diag_units_tile(r0, 0, PR, NB, fu.mu, fu.nu);
-    if (u) {
+    // look-ahead: the critical CTAs hold the rows of the next diagonal block; the next leaf waits for all of them
+    if (critical) {
       __syncthreads();
       if (tid == 0) {
         __threadfence();
-        atomicAdd(fu.flag + 1, u);
+        atomicAdd(fu.flag + 1, 1);
       }
     }
   }
@@ -888,14 +902,19 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
     fu.flag = la.flag;
     fu.mu = rows - n;
     fu.nu = fuse_cols;
+    {
+      const int64_t crit_rows = fuse_cols < rows - n ? fuse_cols : rows - n;   // rows of the next diagonal block
+      fu.ncrit = (int)((crit_rows + PCR - 1) / PCR);
+    }
     GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));
-    la.target = diag_units_total(rows - n, fuse_cols);
+    la.target = fu.ncrit;  // every critical CTA reports once
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
     la.pending = true;
     {
       // work: MACs of the solve (half of rows x 128 x 128: triangular) + the fused K = 128 update
       ProfScope ps(PROF_PANEL, st, (double)(rows - n) * n * (0.5 * n + fuse_cols));
-      const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
+      const int64_t below = rows - n - (int64_t)fu.ncrit * PCR;
+      const unsigned nblk = (unsigned)(fu.ncrit + (below > 0 ? (below + PR - 1) / PR : 0));
       potrf_panel_kernel<<<nblk, 256, panel_smem_bytes(true), st>>>((double*)(A + n * lda), lda, rows - n, (const double*)A, lda,
                                                                      (int)n, (const double*)dblk, em, fu);
       GPK_LAUNCH_OK();

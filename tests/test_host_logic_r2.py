@@ -1,0 +1,117 @@
+"""CPU tests of the host-side logic added in round 2 (no device arithmetic): the triangular packing of the digit-plane
+store, the choice of the number of digit planes, constructor / error behaviour of the widened kernel classes and the
+multi-output plumbing, the bijector chain rule, heteroskedastic likelihood bookkeeping."""
+import numpy as np
+import pytest
+
+import gpflow_b200 as gpf
+from gpflow_b200.base import Parameter, positive
+from gpflow_b200.inducing_variables import (InducingPoints, SeparateIndependentInducingVariables,
+                                            SharedIndependentInducingVariables)
+
+K = gpf.kernels
+
+
+def plane_prefix(rb, nbk):  # mirror of csrc/planes.cuh::plane_prefix
+    q = min(rb, nbk + 1)
+    return 2 * q * (q - 1) + (rb - q) * 4 * nbk
+
+
+def test_plane_store_packing_is_a_bijection_onto_a_dense_range():
+    """Row block rb stores min(4 rb, 4 nbk) k-block tiles; the prefix sums give every (rb, kb) its own slot and leave no
+    holes (csrc/planes.cuh).  Extra row blocks below the square part (rb > nbk) hold all 4 nbk k-blocks."""
+    for nbk in (1, 2, 7, 64):
+        for rbt in (nbk, nbk + 1, nbk + 3):
+            slots = []
+            for rb in range(rbt):
+                nk = min(4 * rb, 4 * nbk)
+                slots += [plane_prefix(rb, nbk) + kb for kb in range(nk)]
+            assert slots == list(range(len(slots)))
+            assert plane_prefix(rbt, nbk) == len(slots)
+    # C2: 8192 + 1 rows -> 65 row blocks of 64 column blocks: 8320 + 256 tiles of S * 4096 bytes
+    assert plane_prefix(66, 64) == 2 * 65 * 64 + 256
+
+
+def pick_slices(cond):  # mirror of csrc/potrf.cu::pick_slices (GPK_TC_SLICES unset)
+    if not cond > 0:
+        return 8
+    return 7 if cond <= 1e4 else (8 if cond <= 3e6 else 0)
+
+
+def test_digit_plane_count_follows_the_conditioning_bound():
+    """Measured with static scales (scripts/static_scale_study.py): max |dL| / max |L| = 1e-11 with S = 7, and every extra plane
+    divides it by 2^7; a pivot of relative size 1 / cond moves by that times cond.  The thresholds keep the relative pivot
+    perturbation below 3e-7 (two orders inside the 1e-5 parity bar)."""
+    assert pick_slices((1.0 + 0.1) / 0.1) == 7          # BASELINE configs[1]
+    assert pick_slices(1e4) == 7 and pick_slices(1.0001e4) == 8
+    assert pick_slices((1 + 1e-6) / 1e-6) == 8           # likelihood variance at its lower bound, unit kernel variance
+    assert pick_slices(1e7) == 0 and pick_slices(0.0) == 8
+    for cond in (1e2, 1e4, 1e6, 3e6):
+        S = pick_slices(cond)
+        assert 1e-11 * 2.0 ** (-7 * (S - 7)) * cond < 3e-7
+
+
+def test_widened_kernel_constructors_and_errors():
+    with pytest.raises(TypeError):
+        K.Periodic(K.Linear())                                          # periodic.py:66-67
+    with pytest.raises(ValueError):
+        K.ArcCosine(order=5)                                            # misc.py:67-68
+    with pytest.raises(ValueError):
+        K.ChangePoints([K.SquaredExponential()], [0.1, 0.2])            # changepoints.py:62-67
+    with pytest.raises(ValueError):
+        K.ChangePoints([K.SquaredExponential(), K.Matern12()], [0.1], steepness=[1.0, 2.0])
+    with pytest.raises(ValueError):
+        K.LinearCoregionalization([K.SquaredExponential()], np.ones((3, 2)))
+    p = K.Periodic(K.Matern32(active_dims=[1, 2]), period=[1.0, 2.0])
+    assert list(p.active_dims) == [1, 2]                                # uses the base kernel's active_dims
+    c = K.Coregion(3, 2)
+    assert c.output_covariance().shape == (3, 3) and np.allclose(c.output_variance(), np.diag(c.output_covariance()))
+    assert not (K.Cosine() + K.SquaredExponential()).is_fusable() and (K.Matern12() * K.White()).is_fusable()
+    cp = K.ChangePoints([K.SquaredExponential(), K.Matern12()], [0.3])
+    assert len(cp.kernels) == 2 and not cp.is_fusable() and len(cp.parameters) >= 6
+    lc = K.LinearCoregionalization([K.SquaredExponential(), K.Matern32()], np.ones((3, 2)))
+    assert lc.num_latent_gps == 2 and len(lc.latent_kernels) == 2
+
+
+def test_multioutput_inducing_variables_and_latent_pairing():
+    from gpflow_b200.covariances import _latent_pairs
+
+    Z = np.zeros((5, 2))
+    sh = SharedIndependentInducingVariables(Z)
+    se = SeparateIndependentInducingVariables([Z, Z + 1, Z + 2])
+    assert sh.num_inducing == 5 and se.num_inducing == 5 and len(se.inducing_variables) == 3
+    ks = [K.SquaredExponential(), K.Matern12(), K.Matern32()]
+    assert len(_latent_pairs(sh, K.SeparateIndependent(ks))) == 3
+    assert len(_latent_pairs(se, K.SharedIndependent(ks[0], 3))) == 3
+    pairs = _latent_pairs(se, K.SeparateIndependent(ks))
+    assert [type(k).__name__ for _, k in pairs] == ["SquaredExponential", "Matern12", "Matern32"]
+    assert all(isinstance(iv, InducingPoints) for iv, _ in pairs)
+    with pytest.raises(ValueError):
+        _latent_pairs(se, K.SeparateIndependent(ks[:2]))
+
+
+def test_bijector_chain_rule_and_unconstrained_assignment():
+    for lower in (None, 1e-6):
+        p = Parameter(0.7, transform=positive(lower=lower) if lower else positive())
+        u = p.unconstrained_variable
+        h = 1e-6
+        fwd = p.transform.forward
+        fd = (fwd(u + h) - fwd(u - h)) / (2 * h)
+        np.testing.assert_allclose(p.unconstrained_gradient(2.0), 2.0 * fd, rtol=1e-8)
+        p.assign_unconstrained(u + 0.3)
+        np.testing.assert_allclose(p.numpy(), fwd(u + 0.3), rtol=1e-14)
+    q = Parameter(np.array([1.0, -2.0]))
+    np.testing.assert_allclose(q.unconstrained_gradient([3.0, 4.0]), [3.0, 4.0])
+
+
+def test_heteroskedastic_gaussian_bookkeeping():
+    lin = gpf.mean_functions.Linear(A=np.array([[0.1]]), b=np.array([0.2]))
+    lik = gpf.likelihoods.Gaussian(variance=lin)
+    assert lik.heteroskedastic and lik.scale is None
+    with pytest.raises(NotImplementedError):
+        lik._variance_value()
+    lik2 = gpf.likelihoods.Gaussian(scale=lin)
+    assert lik2.heteroskedastic and lik2.variance is None
+    assert not gpf.likelihoods.Gaussian(0.3).heteroskedastic
+    with pytest.raises(AssertionError):
+        gpf.likelihoods.Gaussian(0.1, scale=0.2)
