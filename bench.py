@@ -643,10 +643,11 @@ def run_ours(args):
     if f64:
         ach = 2.0 * tc_macs / tc_s / 1e12 if tc_s > 0 else 0.0
         S = int(lib.gpk_potrf_last_slices()) or 7
+        n_digit_mmas = S * (S + 1) // 2 + (1 if S == 6 else 0)   # + the (3,3) product at S = 6 (planes.cuh)
         roofline = {
             "bound": "tensor",
-            "kernel": "syrk_i8_kernel (tcgen05 kind::i8: fp64 operands as S signed 7-bit digit planes, S(S+1)/2 digit "
-                      "MMAs per 32-deep k-step, exact int32 accumulation in TMEM; tcgen05 has no f64 kind)",
+            "kernel": "syrk_i8_kernel (tcgen05 kind::i8: fp64 operands as S balanced base-256 digit planes, S(S+1)/2 "
+                      "(+1 at S = 6) digit MMAs per 32-deep k-step, exact int32 accumulation in TMEM; tcgen05 has no f64 kind)",
             "achieved": ach, "peak": i8_peak, "unit": "TFLOP/s", "frac": ach / i8_peak if i8_peak else None,
             "ops": "int8 operations ISSUED by the launches of this kernel (2 per MAC, padding tiles included) / summed "
                    "duration of those launches (CUDA events on the launch stream)",
@@ -654,8 +655,8 @@ def run_ours(args):
                            "operands resident in shared memory, all SMs); MEASURED_PEAKS.json holds bf16 only",
             "peak_bf16_measured_for_context": {"tflops_sustained": pk["bf16_sustained"], "source": pk["source"],
                                                "frac_vs_2x_bf16": ach / (2.0 * pk["bf16_sustained"])},
-            "slices": S, "digit_mmas_per_fp64_kstep": S * (S + 1) // 2,
-            "fp64_equivalent_tflops": (2.0 * tc_macs / (S * (S + 1) / 2)) / tc_s / 1e12 if tc_s > 0 else 0.0,
+            "slices": S, "digit_radix": 256, "digit_mmas_per_fp64_kstep": n_digit_mmas,
+            "fp64_equivalent_tflops": (2.0 * tc_macs / n_digit_mmas) / tc_s / 1e12 if tc_s > 0 else 0.0,
             "kernel_ms_per_step": prof["tcgen05"]["ms_per_step"], "launches_per_step": prof["tcgen05"]["launches_per_step"],
             "share_of_step": prof["tcgen05"]["ms_per_step"] / ms_step,
             "traffic": ncu.get("syrk_i8_dram_bytes_per_launch"),

@@ -51,45 +51,44 @@ __global__ void row_exp_kernel(const double* __restrict__ A, int64_t lda, int64_
   rowscale[i] = sc;
 }
 
-// dynamic slicing, one warp per row: rows [row0, row0 + nrows) of the k-range [k0, k0 + K) get the scale of their
+// dynamic slicing, one CTA per row: rows [row0, row0 + nrows) of the k-range [k0, k0 + K) get the scale of their
 // running maximum over that range (the extra rows below the square part; every row when GPK_TC_STATIC=0)
 __global__ void __launch_bounds__(256)
 slice_rows_kernel(const double* __restrict__ P, int64_t ld, int64_t row0, int64_t nrows, int64_t k0, int64_t K,
                   TcPlanes pl) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (i >= nrows) return;
+  __shared__ double wmax[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = blockIdx.x;
   const int64_t r = row0 + i;
   const int S = pl.S;
   const double* src = P + i * ld;
   double mx = 0.0;
-  for (int64_t k = lane; k < K; k += 32) mx = fmax(mx, fabs(src[k]));
+  for (int64_t k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(src[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) wmax[warp] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mx = fmax(mx, wmax[w]);
   int e = 0;
   if (mx > 0.0 && mx < 1e300) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
   const double sc = scalbn(1.0, -e + 6);          // x * 2^-e * 2^6
-  if (lane == 0) pl.rowscale[r] = scalbn(1.0, e - 6);
+  if (threadIdx.x == 0) pl.rowscale[r] = scalbn(1.0, e - 6);
   int8_t* rowbase = pl.tile(r >> 7, k0 / TC_KB);
   const int rr = (int)(r & 127);
-  // each lane converts 4 consecutive k per iteration -> one 32-bit store per digit plane
-  for (int64_t kq = lane * 4; kq < K; kq += 128) {
+  const TcDigitizer dz(S);
+  // each thread converts 4 consecutive k per iteration -> one 32-bit store per digit plane
+  for (int64_t kq = (int64_t)threadIdx.x * 4; kq < K; kq += 1024) {
     double v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) v[q] = src[kq + q] * sc;
     const int kb = (int)(kq / TC_KB), kk = (int)(kq % TC_KB);
     int8_t* tb = rowbase + (size_t)kb * S * TC_ATILE + tc_tile_off(rr, kk);
-    for (int s = 0; s < S; ++s) {
-      uint32_t w = 0;
+    uint32_t w[8];
+    tc_digit_words(dz, v, w);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int di;
-        const double d = tc_round_digit(v[q], di);   // |d| <= 64
-        v[q] = (v[q] - d) * 128.0;                   // exact: remainder, rescaled for the next digit
-        w |= (uint32_t)(di & 0xff) << (8 * q);
-      }
-      *reinterpret_cast<uint32_t*>(tb + (size_t)s * TC_ATILE) = w;
-    }
+    for (int j = 0; j < 8; ++j)
+      if (j < S) *reinterpret_cast<uint32_t*>(tb + (size_t)(S - 1 - j) * TC_ATILE) = w[j];
   }
 }
 
@@ -158,6 +157,9 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
   // [32 kb0, 32 (kb0 + KB)) on the diagonal); operands come from the digit-plane store (planes.cuh)
   const double* __restrict__ rowscale = pl.rowscale + rb0 * TC_BM;
   int* err = pl.err;
+  // even S (6): one more accumulator for the (S/2, S/2) digit product (planes.cuh); S = 8 has no TMEM columns left for it
+  constexpr bool SQ = (S == 6);
+  constexpr int H = S / 2, NACC = S + (SQ ? 1 : 0);
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
   constexpr int TC_STAGES = tc_stages(S);   // S = 7: 5 stages of 42 KB, S = 8: 4 of 48 KB, S = 6: 6 of 36 KB
@@ -245,7 +247,7 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
             // A digit planes -> TMEM (columns S*64 .. S*64 + 8S): every A plane is then read from shared
             // memory once per k-step instead of once per MMA (S-s times); tcgen05.cp and tcgen05.mma execute
             // in issue order, so the copy for this k-step queues behind the previous step's MMAs.
-            const uint32_t a_tm = tmem_base + (uint32_t)S * TC_BN;
+            const uint32_t a_tm = tmem_base + (uint32_t)NACC * TC_BN;
 #pragma unroll
             for (int s = 0; s < S; ++s) tc_cp_128x256b(a_tm + s * 8, ad0 + (uint64_t)(s * (TC_ATILE >> 4)));
             if (CAT) {
@@ -256,10 +258,15 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
               for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int t = 0; t + s < S; t += 4) {
-                  const int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  // the square term rides on the MMA of A plane H (B planes 0 .. H instead of 0 .. H-1) except in the first
+                  // k-step, where its accumulator starts from zero while the others of that MMA already hold products
+                  if (SQ && s == H && t == 0 && kb > 0) c = H + 1;
                   tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
                                tc_idesc_n(TC_BN * c), (kb > 0 || s > 0) ? 1u : 0u);
                 }
+              if (SQ && kb == 0)
+                tc_mma_i8_ts(tmem_base + (uint32_t)S * TC_BN, a_tm + H * 8, bd0 + (uint64_t)(H * (TC_BTILE >> 4)), TC_IDESC, 0u);
             } else {
 #pragma unroll
               for (int s = 0; s < S; ++s)
@@ -267,6 +274,9 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
                 for (int t = 0; t + s < S; ++t)
                   tc_mma_i8_ts(tmem_base + (uint32_t)(s + t) * TC_BN, a_tm + s * 8, bd0 + (uint64_t)(t * (TC_BTILE >> 4)),
                                TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+              if (SQ)
+                tc_mma_i8_ts(tmem_base + (uint32_t)S * TC_BN, a_tm + H * 8, bd0 + (uint64_t)(H * (TC_BTILE >> 4)), TC_IDESC,
+                             kb > 0 ? 1u : 0u);
             }
           } else {
             if (CAT) {
@@ -274,10 +284,14 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
               for (int s = 0; s < S; ++s)
 #pragma unroll
                 for (int t = 0; t + s < S; t += 4) {
-                  const int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  int c = (S - s - t) < 4 ? (S - s - t) : 4;
+                  if (SQ && s == H && t == 0 && kb > 0) c = H + 1;  // + the square term (see the TS branch)
                   tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
                             bd0 + (uint64_t)(t * (TC_BTILE >> 4)), tc_idesc_n(TC_BN * c), (kb > 0 || s > 0) ? 1u : 0u);
                 }
+              if (SQ && kb == 0)
+                tc_mma_i8(tmem_base + (uint32_t)S * TC_BN, ad0 + (uint64_t)(H * (TC_ATILE >> 4)),
+                          bd0 + (uint64_t)(H * (TC_BTILE >> 4)), TC_IDESC, 0u);
             } else {
 #pragma unroll
               for (int s = 0; s < S; ++s)
@@ -285,6 +299,9 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
                 for (int t = 0; t + s < S; ++t)
                   tc_mma_i8(tmem_base + (uint32_t)(s + t) * TC_BN, ad0 + (uint64_t)(s * (TC_ATILE >> 4)),
                             bd0 + (uint64_t)(t * (TC_BTILE >> 4)), TC_IDESC, (kb > 0 || s > 0) ? 1u : 0u);
+              if (SQ)
+                tc_mma_i8(tmem_base + (uint32_t)S * TC_BN, ad0 + (uint64_t)(H * (TC_ATILE >> 4)),
+                          bd0 + (uint64_t)(H * (TC_BTILE >> 4)), TC_IDESC, kb > 0 ? 1u : 0u);
             }
           }
           // frees the stage (in every CTA of the cluster) once these copies / MMAs have read it
@@ -342,12 +359,12 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = 0.0;
         double w = 1.0;
-        for (int g = 0; g < S; ++g) {
+        for (int g = 0; g < NACC; ++g) {
           uint32_t v[32];
           tc_ld32(lane_addr + (uint32_t)(g * TC_BN + half * 32), v);
 #pragma unroll
           for (int c = 0; c < 32; ++c) acc[c] = fma(tc_int_to_double((int)v[c]), w, acc[c]);
-          w *= 0.0078125;  // 2^-7
+          w *= 0.00390625;  // 2^-8 (radix 256)
         }
         if (half == 1) {  // accumulators drained: the MMA warp may start the next tile
           tc_fence_before();
@@ -465,7 +482,7 @@ int tc_slice_rows(const double* P, int64_t ld, int64_t row0, int64_t nrows, int6
   if (nrows <= 0) return 0;
   GPK_CHECK_ARG(K % TC_KB == 0 && k0 % TC_KB == 0, "tc_slice_rows: k-range must be a multiple of 32");
   ProfScope ps(PROF_MISC, st);
-  slice_rows_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(P, ld, row0, nrows, k0, K, pl);
+  slice_rows_kernel<<<(unsigned)nrows, 256, 0, st>>>(P, ld, row0, nrows, k0, K, pl);
   GPK_LAUNCH_OK();
   return 0;
 }
@@ -514,7 +531,7 @@ int syrk_tc_planes(double* C, int64_t ldc, int64_t m, int64_t n, const TcPlanes&
   if (grid < 1) return 0;
   const int KBn = (int)(K / TC_KB);
   // issued int8 MACs: every tile of every unit (padding tiles included) x k-steps x S(S+1)/2 digit products
-  ProfScope ps(PROF_TC, st, (double)nunits * cl * KBn * (S * (S + 1) / 2) * (double)(TC_BM * TC_BN * TC_KB));
+  ProfScope ps(PROF_TC, st, (double)nunits * cl * KBn * (S * (S + 1) / 2 + (S == 6 ? 1 : 0)) * (double)(TC_BM * TC_BN * TC_KB));
   auto launch = [&](auto kern) -> int {
     static_cast<void>(0);
     GPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

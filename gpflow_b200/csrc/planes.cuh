@@ -1,8 +1,13 @@
 // planes.cuh — the digit-plane store of one fp64 factorisation (shared by gemm_tc.cu and potrf.cu).
 //
-// The tcgen05 trailing update (gemm_tc.cu) consumes L as S signed 7-bit digit planes per element,
-//     l_ik = 2^(e_i - 6) * sum_s 2^(-7 s) d_s(i,k),   d_s in [-64, 64]  (int8),
-// stored PRE-TILED in the canonical no-swizzle K-major UMMA image: tile (rb, kb) = rows [128 rb, 128 rb + 128) x
+// The tcgen05 trailing update (gemm_tc.cu) consumes L as S signed digit planes per element, radix 256 (round 2; radix 128 in
+// round 1: one more plane for the same precision),
+//     l_ik = 2^(e_i - 6) * sum_s 2^(-8 s) d_s(i,k),   d_0 in [-65, 65], d_s in [-128, 127] (s >= 1)  (int8),
+// i.e. the integer I = rint(l_ik 2^(6 - e_i) 2^(8 (S - 1))) in balanced base 256.  S = 6 resolves 2^-46 of the row scale 2^e_i,
+// S = 7 2^-54 (entries within 2^-2 of 2^e_i keep every bit; as accurate as fp64 arithmetic itself on every matrix of scripts/radix_study.py, cond up to 1e8).  The update
+// keeps the digit products of order s + t < S; for even S it adds the (S/2, S/2) product, the only dropped term of order S
+// whose mean on the diagonal of C is not zero (d^2 > 0 -- it biased sum log diag L by 1e-7 .. 1e-5 at S = 6 without it).
+// Planes are stored PRE-TILED in the canonical no-swizzle K-major UMMA image: tile (rb, kb) = rows [128 rb, 128 rb + 128) x
 // columns [32 kb, 32 kb + 32) holds S consecutive planes of 4096 bytes.  Row block rb only ever needs the k-blocks left
 // of its diagonal block (kb < 4 rb; extra rows below the square part need all of them), so the tiles are packed
 // triangularly: tile (rb, kb) starts at (plane_prefix(rb) + kb) * S * 4096 bytes.
@@ -10,8 +15,8 @@
 // Static scales: |L_ik| <= sqrt(A_ii) for a positive-definite A, so e_i = ilogb(sqrt(A_ii)) + 1 is valid for every
 // entry of row i BEFORE the row exists.  The panel-solve kernel (potrf.cu) therefore emits the planes of the columns it
 // has just finished directly from shared memory, and no slicing pass over L is needed (the price -- rows of L are often
-// well below sqrt(A_ii), so a few leading digit bits are unused -- is measured in scripts/static_scale_study.py:
-// max |dL| / max |L| = 1e-11 at N = 2048 with S = 7).  Rows below the square part (the (Y - m)^T rows that ride along)
+// well below sqrt(A_ii), so a few leading digit bits are unused -- is measured in scripts/static_scale_study.py and
+// scripts/radix_study.py: max |dL| / max |L| = 2e-11 at S = 6, 1e-13 at S = 7 on BASELINE configs[1]).  Rows below the square part (the (Y - m)^T rows that ride along)
 // have no such bound and are sliced with their running row maximum before each update (slice_rows_kernel).
 #pragma once
 #include "common.cuh"
@@ -39,11 +44,60 @@ __device__ __host__ __forceinline__ int64_t plane_prefix(int64_t rb, int64_t nbk
 //  * digit extraction: t = v + 1.5 * 2^52 rounds v (|v| < 2^31) to the nearest integer (ties to even, like rint) in the
 //    fp64 adder; the integer sits in the low word of t, the rounded value is t - 1.5 * 2^52;
 //  * int32 -> double: the bit pattern 0x43300000'(x ^ 0x80000000) is 2^52 + 2^31 + x exactly.
-__device__ __forceinline__ double tc_round_digit(double v, int& digit) {
-  const double magic = 6755399441055744.0;  // 1.5 * 2^52
-  const double t = v + magic;
-  digit = __double2loint(t);
-  return t - magic;
+constexpr int TC_RADIX_BITS = 8;
+// The S balanced base-256 digits of I = rint(v 2^(8 (S - 1))), |v| < 64: d_s in [-128, 127] for s >= 1, the top digit d_0
+// is what remains (|d_0| <= 65).  Adding the bias J = I + 0x80...80 (S - 1 bytes) makes every lower digit an unsigned byte
+// u_s = d_s + 128 of J, and u_s ^ 0x80 is d_s as an int8; J >> 8 (S - 1) is d_0.  So the digit bytes of one value are
+//     X = (I + flip) ^ flip,  flip = 0x80 repeated S - 1 times,  byte j of X = digit of plane S - 1 - j,
+// and I comes out of the fp64 adder without a conversion instruction: the bit pattern of x + 1.5 2^52 is
+// 0x433 << 52 | (2^51 + rint(x)) for |x| < 2^51 (S <= 6: |I| <= 2^46).  S >= 7 (|I| <= 2^54, 2^62) rounds the top 22 bits
+// and the rest separately: hi = rint(v 2^16) (exact remainder r = v 2^16 - hi, |r| <= 1/2), I = hi 2^low + rint(r 2^low).
+// 5 instructions per value at S <= 6, 11 at S >= 7 (a digit-by-digit loop costs ~10 per DIGIT).
+struct TcDigitizer {
+  double up;                     // 2^(8 (S - 1)) (S <= 6) or 2^low (S >= 7), low = 8 (S - 1) - 16
+  unsigned long long c, flip;    // c = flip - (0x433 << 52) - 2^51
+  int S, hshift;                 // S >= 7: hi enters at bit low = 32 + hshift
+  __device__ __forceinline__ explicit TcDigitizer(int S_) : S(S_) {
+    const int low = S <= 6 ? TC_RADIX_BITS * (S - 1) : TC_RADIX_BITS * (S - 1) - 16;
+    up = __hiloint2double((1023 + low) << 20, 0);
+    hshift = S <= 6 ? 0 : low - 32;
+    flip = 0x8080808080808080ull >> (8 * (9 - S));
+    c = flip - 0x4330000000000000ull - 0x0008000000000000ull;
+  }
+  __device__ __forceinline__ unsigned long long bytes(double v) const {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    if (S <= 6) {
+      const double t = fma(v, up, magic);
+      return ((unsigned long long)__double_as_longlong(t) + c) ^ flip;
+    }
+    const double xh = v * 65536.0;
+    const double th = xh + magic;             // low word = rint(v 2^16) as an int32
+    const double r = xh - (th - magic);
+    const double t2 = fma(r, up, magic);
+    unsigned long long J = (unsigned long long)__double_as_longlong(t2) + c;
+    J += (unsigned long long)(long long)__double2loint(th) << (32 + hshift);
+    return J ^ flip;
+  }
+};
+// 4 x 4 byte transpose: o[j] = byte j of a0 | byte j of a1 << 8 | byte j of a2 << 16 | byte j of a3 << 24 (8 PRMT)
+__device__ __forceinline__ void tc_transpose4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t (&o)[4]) {
+  const uint32_t l01 = __byte_perm(a0, a1, 0x5140), h01 = __byte_perm(a0, a1, 0x7362);
+  const uint32_t l23 = __byte_perm(a2, a3, 0x5140), h23 = __byte_perm(a2, a3, 0x7362);
+  o[0] = __byte_perm(l01, l23, 0x5410);
+  o[1] = __byte_perm(l01, l23, 0x7632);
+  o[2] = __byte_perm(h01, h23, 0x5410);
+  o[3] = __byte_perm(h01, h23, 0x7632);
+}
+// digit words of 4 consecutive k of one row: w[j] = the 32-bit word of plane S - 1 - j (j < S)
+__device__ __forceinline__ void tc_digit_words(const TcDigitizer& dz, const double (&v)[4], uint32_t (&w)[8]) {
+  unsigned long long x[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) x[q] = dz.bytes(v[q]);
+  uint32_t lo[4], hi[4];
+  tc_transpose4((uint32_t)x[0], (uint32_t)x[1], (uint32_t)x[2], (uint32_t)x[3], lo);
+  tc_transpose4((uint32_t)(x[0] >> 32), (uint32_t)(x[1] >> 32), (uint32_t)(x[2] >> 32), (uint32_t)(x[3] >> 32), hi);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { w[j] = lo[j]; w[4 + j] = hi[j]; }
 }
 __device__ __forceinline__ double tc_int_to_double(int x) {
   return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;  // 2^52 + 2^31

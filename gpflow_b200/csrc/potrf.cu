@@ -599,6 +599,7 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     if (!(em.pl.planes && nb == NB)) return;
     if (!fu.C) __syncthreads();  // (the fused path has passed a barrier already) all warps' rows are in Bs
     const int S = em.pl.S;
+    const TcDigitizer dz(S);
 #pragma unroll 1
     for (int e = tid; e < nrows_cta * 8; e += 256) {
       const int rl = e % nrows_cta, ch = e / nrows_cta;  // local row, 16-column chunk
@@ -614,17 +615,16 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
       }
       const int64_t kcol = em.col_g0 + ch * 16;
       int8_t* tb = em.pl.tile(grow >> 7, kcol / TC_KB) + tc_tile_off((int)(grow & 127), (int)(kcol % TC_KB));
-      for (int s2 = 0; s2 < S; ++s2) {
-        uint32_t wd[4] = {0u, 0u, 0u, 0u};
+      // digit bytes of every value (planes.cuh), 4 x 4 byte transposes, then one 16-byte store per plane
+      uint32_t wd[4][8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          int di;
-          const double d = tc_round_digit(v[u], di);
-          v[u] = (v[u] - d) * 128.0;
-          wd[u >> 2] |= (uint32_t)(di & 0xff) << (8 * (u & 3));
-        }
-        *reinterpret_cast<uint4*>(tb + (size_t)s2 * TC_ATILE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      for (int g = 0; g < 4; ++g) {
+        const double v4[4] = {v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]};
+        tc_digit_words(dz, v4, wd[g]);
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < S) *reinterpret_cast<uint4*>(tb + (size_t)(S - 1 - j) * TC_ATILE) = make_uint4(wd[0][j], wd[1][j], wd[2][j], wd[3][j]);
     }
   };
   // CTAs that hold rows of the next diagonal block update and publish them first (the next leaf is waiting for them) and
@@ -819,9 +819,9 @@ template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, int64_t col0,
                            LookAhead& la, cudaStream_t st) {
   GemmOpts opts;
-  // int32 accumulators: 64 * 64 * K * S < 2^31 (tests/test_digit_slicing_model.py); deeper updates use DMMA
+  // int32 accumulators: 128 * 128 * K * S < 2^31 (radix-256 digits; tests/test_digit_slicing_model.py); deeper updates use DMMA
   const bool use_tc = sizeof(T) == 8 && la.pl.planes && K >= tc_min_k() && K % 32 == 0 && n <= m &&
-                      K * la.pl.S * 4096 < (1ll << 31);
+                      K * la.pl.S * 16384 < (1ll << 31);
   if (use_tc) {
     // operand rows without a static scale: the extra rows below the square part (or every row, GPK_TC_STATIC=0)
     const int64_t r0 = col0 + K;
@@ -961,21 +961,19 @@ static bool slim_enabled() {
   return v == 1;
 }
 
-// Number of digit planes of the tcgen05 trailing updates from what the caller knows about the conditioning
-// (cond = max_i A_ii / lambda_min, e.g. (kernel variance + noise) / noise for GPR).  The digit truncation perturbs the
-// trailing matrix by ~1e-11 max_i A_ii with S = 7 and static scales (scripts/static_scale_study.py), i.e. pivots by
-// ~1e-11 cond relative: S = 7 keeps that below 1e-7 up to cond 1e4, S = 8 (2^7 finer) up to ~1e6.5, beyond that the
-// updates run on fp64 DMMA (return 0).  Unknown conditioning (a bare gpk_potrf) takes S = 8.  GPK_TC_SLICES pins S.
+// Number of base-256 digit planes of the tcgen05 trailing updates from what the caller knows about the conditioning
+// (cond = max_i A_ii / lambda_min, e.g. (kernel variance + noise) / noise for GPR).  Measured with the NumPy emulation
+// of this factorisation (scripts/radix_study.py; numerically low-rank matrices, static scales): S = 6 (+ the (3,3) product)
+// moves L by ~1e-12 cond relative and the LML by <= 2e-8 relative up to cond 1e4; S = 7 resolves 2^-54 of the row scale and
+// stays within ~3x of plain fp64 arithmetic for every conditioning tried (1e1 .. 1e8), so it serves everything else,
+// including an unknown conditioning (a bare gpk_potrf).  GPK_TC_SLICES pins S (6 .. 8).
 static int g_last_slices = 0;  // diagnostic: digit planes of the most recent fp64 factorisation (0 = DMMA / none)
 int potrf_last_slices() { return g_last_slices; }
 
 static int pick_slices(double cond_hint) {
   const int pinned = tc_slices();
   if (pinned) return pinned;
-  if (!(cond_hint > 0.0)) return 8;
-  if (cond_hint <= 1.0e4) return 7;
-  if (cond_hint <= 3.0e6) return 8;
-  return 0;
+  return (cond_hint > 0.0 && cond_hint <= 1e4) ? 6 : 7;
 }
 
 template <typename T>

@@ -34,6 +34,10 @@ def digits(P, e, S, bits):
     return D
 
 
+SQUARE_TERM = False   # even S: also keep the (S/2, S/2) digit product -- the only dropped order-S term with a non-zero mean
+                      # on the diagonal of C (d^2 > 0), i.e. the systematic part of the error of sum log diag L
+
+
 def sliced_update(C, P, n, e_rows, S, bits):
     m = P.shape[0]
     D = digits(P, e_rows, S, bits)
@@ -45,6 +49,8 @@ def sliced_update(C, P, n, e_rows, S, bits):
             a += D[s] @ D[g - s][:n].T
         assert np.abs(a).max() < 2 ** 31
         acc += a * 2.0 ** (-bits * g)
+    if SQUARE_TERM and S % 2 == 0:
+        acc += (D[S // 2] @ D[S // 2][:n].T) * 2.0 ** (-bits * S)
     C -= acc * rs[:, None] * rs[None, :n]
 
 
@@ -94,7 +100,8 @@ if __name__ == "__main__":
     print(f"N = {N}; columns: max|dL|/max|L|, |d sum log diag L|, relative LML error")
     for noise in (1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8):
         row = [f"noise {noise:.0e} (cond ~ {(1 + noise) / noise:.1e})"]
-        for bits, S in ((0, 0), (7, 7), (7, 8), (8, 6), (8, 7), (8, 8)):
+        for bits, S, sq in ((0, 0, 0), (7, 7, 0), (7, 8, 0), (8, 6, 0), (8, 6, 1), (8, 7, 0), (8, 8, 0)):
+            SQUARE_TERM = bool(sq)
             eL, dl, rl = run(N, noise, S, bits, hard)
-            row.append(f"{'fp64' if not S else f'r{1 << bits} S={S}'}: {eL:.1e} {dl:.1e} {rl:.1e}")
+            row.append(f"{'fp64' if not S else f'r{1 << bits} S={S}' + ('+sq' if sq else '')}: {eL:.1e} {dl:.1e} {rl:.1e}")
         print(" | ".join(row))

@@ -26,7 +26,7 @@ def test_gpr_noise_at_lower_bound_long_lengthscale(cuda_device, N):
     m = gpf.models.GPR((d["X"], d["Y"]), kp, likelihood=gpf.likelihoods.Gaussian(s2 * (1 + 1e-9)))
     s2 = float(m.likelihood.variance.numpy())
     lml = float(m.log_marginal_likelihood())
-    assert _lib.load().gpk_potrf_last_slices() == 8  # cond hint (1 + s2) / s2 = 1e6 -> 8 digit planes
+    assert _lib.load().gpk_potrf_last_slices() == 7  # cond hint (1 + s2) / s2 = 1e6 -> 7 base-256 digit planes
     ref = O.gpr_log_marginal_likelihood(d["X"], d["Y"], ko, s2)
     np.testing.assert_allclose(lml, ref, rtol=1e-5)
     mean, var = m.predict_f(d["Xnew"])
@@ -36,11 +36,11 @@ def test_gpr_noise_at_lower_bound_long_lengthscale(cuda_device, N):
 
 
 def test_gpr_engine_follows_conditioning_hint(cuda_device):
-    """(kernel variance + noise) / noise selects S = 7 (<= 1e4), S = 8 (<= 3e6) or the DMMA engine; all agree with the
-    oracle at the model tolerance."""
+    """(kernel variance + noise) / noise selects S = 6 base-256 digit planes (<= 1e4) or S = 7 (as accurate as fp64
+    arithmetic: no DMMA fallback); all agree with the oracle at the model tolerance."""
     d = O.make_data(2, 1536, 8, 1)
     lib = _lib.load()
-    for s2, want in ((0.1, 7), (1e-5, 8), (2e-7, 0)):
+    for s2, want in ((0.1, 6), (1e-5, 7), (2e-7, 7)):
         kp, ko = gpf.kernels.Matern52(lengthscales=3.0), O.Matern52(lengthscales=3.0)
         m = gpf.models.GPR((d["X"], d["Y"]), kp, likelihood=gpf.likelihoods.Gaussian(s2, variance_lower_bound=1e-7))
         lml = float(m.log_marginal_likelihood())
