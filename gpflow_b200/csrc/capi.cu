@@ -115,6 +115,13 @@ int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* str
   return leaf_debug((double*)A, lda, n, (double*)dinv, (long long*)dbg, (cudaStream_t)stream);
 }
 
+int gpk_debug_trace(void* buf, void* pos, unsigned int capacity) {
+  TraceBuf tb{(unsigned long long*)buf, (unsigned int*)pos, buf ? capacity : 0u};
+  GPK_TRY(trace_set_potrf(tb));
+  GPK_TRY(trace_set_tc(tb));
+  return 0;
+}
+
 int gpk_prof_enable(int on) {
   for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_recs.clear();

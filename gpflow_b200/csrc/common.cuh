@@ -12,6 +12,31 @@
 
 namespace gpk {
 
+// ---- device timeline (tuning aid, gpk_debug_trace): %globaltimer stamps written by thread 0 of selected CTAs ------------------
+// Every translation unit that marks has its own copy of g_trace (no relocatable device code); trace_set_* install the buffer.
+struct TraceBuf {
+  unsigned long long* buf;  // pairs (time in ns, id << 8 | phase)
+  unsigned int* pos;
+  unsigned int cap;
+};
+#ifdef __CUDACC__
+static __device__ TraceBuf g_trace;
+__device__ __forceinline__ void trace_mark(int id, int phase) {
+  if (g_trace.buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(g_trace.pos, 1u);
+    if (i < g_trace.cap) {
+      g_trace.buf[2 * i] = t;
+      g_trace.buf[2 * i + 1] = ((unsigned long long)id << 8) | (unsigned)phase;
+    }
+  }
+}
+#endif
+int trace_set_potrf(TraceBuf tb);
+int trace_set_tc(TraceBuf tb);
+
+
 void set_error(const char* fmt, ...);
 void count_launch();
 

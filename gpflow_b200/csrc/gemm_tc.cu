@@ -17,7 +17,7 @@
 // Pipeline (per persistent CTA, 192 threads):
 //   warp 0   producer : cp.async.bulk (1-D TMA) of PRE-TILED digit planes global -> shared, mbarrier
 //   warp 1   issuer   : one elected lane issues tcgen05.mma (SS, no-swizzle K-major descriptors)
-//   warps 2-5 epilogue: tcgen05.ld TMEM -> registers, recombine, read-modify-write C
+//   warps 2-5 epilogue: tcgen05.ld TMEM -> registers, recombine, bulk reduction (add) of the update into C
 // The slicing pre-pass (slice_rows_kernel) writes the digit planes directly in the canonical UMMA
 // shared-memory image (8x16-byte core matrices), so a stage is filled by plain bulk copies: no tensor
 // map, no swizzle to keep consistent between three places.
@@ -29,7 +29,11 @@
 
 namespace gpk {
 
-constexpr int TC_SMEM_BUDGET = 220 * 1024;  // pipeline stages: as many as fit (S planes of A and B per stage, tightly packed)
+// Epilogue staging: every epilogue thread owns one row of 32 doubles (256 B, rows 272 B apart: 16-byte stores of a quarter
+// warp then hit 32 different banks) from which a bulk reduction adds its half row of the update into C.
+constexpr int TC_EPI_ROW = 272;
+constexpr int TC_EPI_BYTES = 128 * TC_EPI_ROW;
+constexpr int TC_SMEM_BUDGET = 226 * 1024 - TC_EPI_BYTES;  // pipeline stages: as many as fit (S planes of A and B per stage, tightly packed)
 __host__ __device__ constexpr int tc_stages(int S) { return TC_SMEM_BUDGET / (S * (TC_ATILE + TC_BTILE)) > 6 ? 6 : TC_SMEM_BUDGET / (S * (TC_ATILE + TC_BTILE)); }
 constexpr int TC_TMEM_COLS = 512;
 
@@ -57,39 +61,8 @@ __global__ void __launch_bounds__(256)
 slice_rows_kernel(const double* __restrict__ P, int64_t ld, int64_t row0, int64_t nrows, int64_t k0, int64_t K,
                   TcPlanes pl) {
   __shared__ double wmax[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = blockIdx.x;
-  const int64_t r = row0 + i;
-  const int S = pl.S;
-  const double* src = P + i * ld;
-  double mx = 0.0;
-  for (int64_t k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(src[k]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) wmax[warp] = mx;
-  __syncthreads();
-#pragma unroll
-  for (int w = 0; w < 8; ++w) mx = fmax(mx, wmax[w]);
-  int e = 0;
-  if (mx > 0.0 && mx < 1e300) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
-  const double sc = scalbn(1.0, -e + 6);          // x * 2^-e * 2^6
-  if (threadIdx.x == 0) pl.rowscale[r] = scalbn(1.0, e - 6);
-  int8_t* rowbase = pl.tile(r >> 7, k0 / TC_KB);
-  const int rr = (int)(r & 127);
-  const TcDigitizer dz(S);
-  // each thread converts 4 consecutive k per iteration -> one 32-bit store per digit plane
-  for (int64_t kq = (int64_t)threadIdx.x * 4; kq < K; kq += 1024) {
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = src[kq + q] * sc;
-    const int kb = (int)(kq / TC_KB), kk = (int)(kq % TC_KB);
-    int8_t* tb = rowbase + (size_t)kb * S * TC_ATILE + tc_tile_off(rr, kk);
-    uint32_t w[8];
-    tc_digit_words(dz, v, w);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < S) *reinterpret_cast<uint32_t*>(tb + (size_t)(S - 1 - j) * TC_ATILE) = w[j];
-  }
+  tc_slice_row_cta(P + i * ld, row0 + i, k0, K, pl, wmax);
 }
 
 // shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B (next 16-byte k chunk),
@@ -164,7 +137,8 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
   constexpr uint32_t stage_bytes = (uint32_t)S * (TC_ATILE + TC_BTILE);
   constexpr int TC_STAGES = tc_stages(S);   // S = 7: 5 stages of 42 KB, S = 8: 4 of 48 KB, S = 6: 6 of 36 KB
   constexpr uint32_t stage_stride = (uint32_t)S * (TC_ATILE + TC_BTILE);
-  uint8_t* bar_area = tc_smem + TC_STAGES * (size_t)stage_stride;
+  uint8_t* epi_area = tc_smem + TC_STAGES * (size_t)stage_stride;  // [128][TC_EPI_ROW]
+  uint8_t* bar_area = epi_area + TC_EPI_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bar_area);  // full[4], empty[4], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +147,7 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
   const uint32_t tfull = smem_u32(bars + 2 * TC_STAGES), tempty = smem_u32(bars + 2 * TC_STAGES + 1);
 
   if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) trace_mark(4, 0);
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, CL);  // every CTA of the cluster releases a stage (A is multicast into all)
@@ -192,6 +167,7 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
   if (CL > 1) cluster_sync_all();  // peer barriers initialised before any multicast copy / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0 && blockIdx.x == 0) trace_mark(4, 10);  // prologue done (barriers, TMEM, cluster sync)
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
@@ -316,45 +292,34 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
     }
   } else {
     // ===== epilogue (4 warps = 128 TMEM lanes) =====
-    // One thread = one row of the tile.  The 32-column segments of C are fetched into registers with 16-byte loads
-    // BEFORE the accumulators are waited for / read (the latency hides behind the mainloop and the TMEM drain), the
-    // column scales come through the read-only path, and the accumulators are handed back to the MMA warp as soon as
-    // the last TMEM read is done -- the stores of the second half overlap the next tile's first MMAs.
-    // (An element-wise `crow[c] -= rs * rowscale[col] * acc[c]` serialises on 64 dependent global loads per row when
-    // the compiler cannot prove that the scales do not alias C: 13% of the int8 peak, ncu long_scoreboard.)
+    // One thread = one row of the tile.  Per 32-column half: drain the accumulators (tcgen05.ld), recombine the digit orders
+    // in fp64, scale, write the half row of the UPDATE (-rs cs acc) into the thread's own 256-byte row of the staging
+    // buffer and let a bulk reduction (cp.reduce.async.bulk .add.f64) add it into C in L2.  C is never read by the SM, the
+    // global traffic is whole 256-byte row segments issued by the copy engine, and everything is thread-local (a thread's
+    // fence.proxy.async orders its own shared-memory stores before its own bulk operation).  Every element of C receives
+    // exactly one reduction per launch, so the result does not depend on any ordering.
+    // (The previous read-modify-write epilogue -- 16-byte loads / stores of a thread's own row, 32 lines per warp
+    // instruction -- took 7.7 us per tile on the LSU: profiles/r2/trace_c2_phases.csv.)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     TcTileIter it(m, n, lower, CL, rank);
     uint32_t tph = 0;
     const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    double* srow = reinterpret_cast<double*>(epi_area + (size_t)(q * 32 + lane) * TC_EPI_ROW);
+    const uint32_t srow_s = smem_u32(srow);
     while (it.next()) {
       const int64_t row = it.tm * TC_BM + q * 32 + lane;
       const int64_t colb = it.tn * TC_BN;
       const bool live = row < m && it.valid();
       const bool fullw = vec_ok && colb + TC_BN <= n;
       double* crow = C + (live ? row : 0) * ldc + colb;
-      const double rs = live ? __ldg(rowscale + row) : 0.0;
+      const double rs = live ? -__ldg(rowscale + row) : 0.0;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      double cv[32];
-      auto fetch_c = [&](int half) {
-        if (!live) return;
-        if (fullw) {
-#pragma unroll
-          for (int c2 = 0; c2 < 16; ++c2) {
-            const double2 t2 = *reinterpret_cast<const double2*>(crow + half * 32 + 2 * c2);
-            cv[2 * c2] = t2.x;
-            cv[2 * c2 + 1] = t2.y;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) cv[c] = (colb + half * 32 + c < n) ? crow[half * 32 + c] : 0.0;
-        }
-      };
-      fetch_c(0);
       mbar_wait(tfull, tph, err, 104);
       tc_fence_after();
+      const bool tr0 = blockIdx.x == 0 && tph == 0 && threadIdx.x == 64 && it.is_head();  // (first tile of CTA 0: timeline marks)
+      if (tr0) trace_mark(4, 13);  // accumulators complete
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        if (half == 1) fetch_c(1);
         double acc[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = 0.0;
@@ -370,39 +335,52 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
           tc_fence_before();
           mbar_arrive(tempty);
         }
-        if (live) {
-          const double* sc = rowscale + colb + half * 32;
-          if (fullw) {
+        if (tr0) trace_mark(4, 14 + 2 * half);  // TMEM drained + converted (14 / 16)
+        const double* sc = rowscale + colb + half * 32;
+        if (fullw) {
+          // the bulk reduction issued from this row two halves ago has finished READING the staging row
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #pragma unroll
-            for (int c2 = 0; c2 < 16; ++c2) {
-              const double2 s2 = __ldg(reinterpret_cast<const double2*>(sc + 2 * c2));
-              double2 o;
-              o.x = fma(-rs * s2.x, acc[2 * c2], cv[2 * c2]);
-              o.y = fma(-rs * s2.y, acc[2 * c2 + 1], cv[2 * c2 + 1]);
-              *reinterpret_cast<double2*>(crow + half * 32 + 2 * c2) = o;
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (colb + half * 32 + c < n) crow[half * 32 + c] = fma(-rs * __ldg(sc + c), acc[c], cv[c]);
+          for (int c2 = 0; c2 < 16; ++c2) {
+            const double2 s2 = __ldg(reinterpret_cast<const double2*>(sc + 2 * c2));
+            double2 o;
+            o.x = (rs * s2.x) * acc[2 * c2];
+            o.y = (rs * s2.y) * acc[2 * c2 + 1];
+            *reinterpret_cast<double2*>(srow + 2 * c2) = o;
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (live)
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 256;" ::"l"(crow + half * 32),
+                         "r"(srow_s)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (live) {  // ragged right edge / unaligned C: element-wise read-modify-write (rare)
+#pragma unroll
+          for (int c = 0; c < 32; ++c)  // (fully unrolled: a runtime index would move acc[] to local memory)
+            if (colb + half * 32 + c < n) crow[half * 32 + c] = fma(rs * __ldg(sc + c), acc[c], crow[half * 32 + c]);
         }
+        if (tr0) trace_mark(4, 15 + 2 * half);  // update issued (15 / 17)
       }
       tph ^= 1;
-      if (head_flag && it.is_head()) {  // publish this head tile once all four epilogue warps stored it
+      if (head_flag && it.is_head()) {  // publish this head tile once all four epilogue warps' reductions are complete
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // the reductions (async proxy) before the generic-proxy release below
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) {
           __threadfence();
+          trace_mark(4, 1);  // a head tile published
           atomicAdd(head_flag, 1);
           const int u = diag_units_tile(it.tm * TC_BM, it.tn * TC_BN, TC_BM, TC_BN, m, n);
           if (u) atomicAdd(head_flag + 1, u);  // progress on the next diagonal block
         }
       }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the staging rows stay valid until every reduction has read them
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_mark(4, blockIdx.x == 0 ? 2 : 3);
   if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
@@ -423,6 +401,11 @@ int tc_slices() {
     if (s > TC_MAXS) s = TC_MAXS;
   }
   return s;
+}
+
+int trace_set_tc(TraceBuf tb) {
+  GPK_CUDA_OK(cudaMemcpyToSymbol(g_trace, &tb, sizeof(tb)));
+  return 0;
 }
 
 bool tc_enabled() {
@@ -507,7 +490,7 @@ int syrk_tc_planes(double* C, int64_t ldc, int64_t m, int64_t n, const TcPlanes&
                 "syrk_tc: unsupported shape m=%lld n=%lld K=%lld r0=%lld k0=%lld", (long long)m, (long long)n, (long long)K,
                 (long long)r0, (long long)k0);
   const int64_t rb0 = r0 / TC_BM, kb0 = k0 / TC_KB;
-  const size_t smem = tc_stages(S) * (size_t)S * (TC_ATILE + TC_BTILE) + 256;
+  const size_t smem = tc_stages(S) * (size_t)S * (TC_ATILE + TC_BTILE) + TC_EPI_BYTES + 256;
   // Both operands from shared memory with the digit products of one A plane CONCATENATED along N (one MMA of N up to 256
   // instead of up to four of N = 64): scripts/mb_mma.cu measures 52.9 cycles per N = 64 SS MMA against a floor of 32,
   // but 128.0 per N = 256 MMA (= the floor), and the tcgen05.cp of the TS form costs 137 cycles per k-step on top.

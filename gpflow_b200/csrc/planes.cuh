@@ -118,6 +118,43 @@ struct TcPlanes {
   }
 };
 
+// Dynamic slicing of ONE row by a whole CTA (256 threads): the k-range [k0, k0 + K) of row r (src = &row[k0]) gets the scale
+// of its maximum over that range -- the rows below the square part have no static bound.  wmax: 8 doubles of shared memory.
+__device__ __forceinline__ void tc_slice_row_cta(const double* src, int64_t r, int64_t k0, int64_t K, const TcPlanes& pl,
+                                                 double* wmax) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = pl.S;
+  double mx = 0.0;
+  for (int64_t k = threadIdx.x; k < K; k += 256) mx = fmax(mx, fabs(src[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();  // (wmax may still be read by the previous row's threads)
+  if (lane == 0) wmax[warp] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mx = fmax(mx, wmax[w]);
+  int e = 0;
+  if (mx > 0.0 && mx < 1e300) e = ilogb(mx) + 1;  // mx * 2^-e in [0.5, 1)
+  const double sc = scalbn(1.0, -e + 6);          // x * 2^-e * 2^6
+  if (threadIdx.x == 0) pl.rowscale[r] = scalbn(1.0, e - 6);
+  int8_t* rowbase = pl.tile(r >> 7, k0 / TC_KB);
+  const int rr = (int)(r & 127);
+  const TcDigitizer dz(S);
+  // each thread converts 4 consecutive k per iteration -> one 32-bit store per digit plane
+  for (int64_t kq = (int64_t)threadIdx.x * 4; kq < K; kq += 1024) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = src[kq + q] * sc;
+    const int kb = (int)(kq / TC_KB), kk = (int)(kq % TC_KB);
+    int8_t* tb = rowbase + (size_t)kb * S * TC_ATILE + tc_tile_off(rr, kk);
+    uint32_t w[8];
+    tc_digit_words(dz, v, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < S) *reinterpret_cast<uint32_t*>(tb + (size_t)(S - 1 - j) * TC_ATILE) = w[j];
+  }
+}
+
 size_t tc_planes_bytes(int64_t n, int64_t rows);
 TcPlanes tc_planes_layout(void* ws, int64_t n, int64_t rows, int S);
 // rowscale[i] = 2^(ilogb(sqrt(A_ii)) + 1 - 6) for the square rows (reads the ORIGINAL diagonal: call before factorising)

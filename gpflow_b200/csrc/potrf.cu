@@ -22,6 +22,7 @@
 #include <utility>
 
 #include "common.cuh"
+#include <type_traits>
 #include "planes.cuh"
 
 namespace gpk {
@@ -39,6 +40,20 @@ template <> __device__ __forceinline__ float sqrt_t<float>(float x) { return sqr
 //    warp touch consecutive rows of the stride-129 array: bank-conflict free;
 //  * the serial part (32x32 diagonal Cholesky, one warp) keeps its row in registers and exchanges
 //    columns by shuffles.
+
+// asynchronous global -> shared copies (all of a thread's copies in flight at once; cp_async_wait_all + a barrier publish them)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {  // !valid: 16 zero bytes
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {  // one element (4 or 8 bytes)
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
 // fp32 MUFU.RSQ seed + two Newton steps in fp64 (relative error ~2^-52): ~2/3 of the latency of the
@@ -274,21 +289,18 @@ __device__ void invert_offdiag_128(T* S, T* tmp, bool level64 = true) {
   }
 }
 
-// coalesced, 32-deep unrolled load of the lower triangle of an n x n block (identity-padded to 128)
+// lower triangle of an n x n block (identity-padded to 128) as asynchronous element copies: every thread has its up to 64
+// loads in flight at once (the row stride 129 rules out 16-byte copies); the caller's barrier follows cp_async_wait_all
 template <typename T>
 __device__ __forceinline__ void load_lower_block(T* S, const T* __restrict__ A, int64_t lda, int n) {
   const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;  // 2 rows per pass
-#pragma unroll 1
-  for (int r0 = 0; r0 < NB; r0 += 64) {
-    T v[32];
-#pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int r = r0 + 2 * u + rh;
-      v[u] = (r < n && c <= r) ? A[(int64_t)r * lda + c] : ((r >= n && c == r) ? T(1) : T(0));
-    }
-#pragma unroll
-    for (int u = 0; u < 32; ++u) S[(r0 + 2 * u + rh) * LS + c] = v[u];
+#pragma unroll 8
+  for (int u = 0; u < 64; ++u) {
+    const int r = 2 * u + rh;
+    if (r < n && c <= r) cp_async_elem<T>(S + r * LS + c, A + (int64_t)r * lda + c);
+    else S[r * LS + c] = (r >= n && c == r) ? T(1) : T(0);
   }
+  cp_async_wait_all();
 }
 
 template <typename T>
@@ -334,6 +346,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   const int tr = tid >> 3, tc = tid & 7;   // 32 x 8 thread grid, interleaved 4x4 micro-tiles
 
 #define GPK_DBG(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+  if (tid == 0 && blockIdx.x == 0) trace_mark(1, 0);
   if (wait_flag) {  // look-ahead: the trailing update still running on the main stream publishes its
     if (tid == 0) { // head tiles (this block's inputs) through a counter; bounded spin, never a hang
       unsigned spins = 0;
@@ -346,6 +359,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
     __syncthreads();
   }
   GPK_DBG(0);
+  if (tid == 0 && blockIdx.x == 0) trace_mark(1, 1);  // inputs ready
   load_lower_block<T>(S, A, lda, n);
   __syncthreads();
   GPK_DBG(1);
@@ -446,6 +460,7 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   if (SLIM) write_dinv64<T>(S, dinv); else write_dinv<T>(S, dinv);
   __syncthreads();
   GPK_DBG(9);
+  if (tid == 0 && blockIdx.x == 0) trace_mark(1, 2);
 #undef GPK_DBG
 }
 
@@ -474,13 +489,16 @@ struct PanelEmit {
   TcPlanes pl;        // pl.planes == nullptr: off
   int64_t row_g0;     // global row index of B's first row
   int64_t col_g0;     // global column index of the block
+  int64_t dyn_k0;     // dyn_K > 0: the tcgen05 update of the k-range [dyn_k0, dyn_k0 + dyn_K) follows this panel (it ends at
+  int64_t dyn_K;      // this block); the CTAs that own rows below the square part slice them for it (dynamic scales)
 };
 constexpr int PCR = 16;  // rows per CRITICAL CTA of the fused panel (see the row mapping in the kernel)
 struct PanelFuse {
   double* C;          // nullptr: off.  C[rows, uc] (same rows as B), leading dimension ldb
   int uc;             // columns of the update (<= 128)
   int ncrit;          // CTAs (PCR rows each) that cover the first uc rows = X_top = the next diagonal block
-  int* flag;          // [1]: 32x32 units of the next diagonal block done, [2]: X_top CTAs finished
+  int* flag;          // [1]: 32x32 units of the next diagonal block done, [2]: X_top CTAs finished (never reset during a
+  int xtop_target;    // factorisation: waits compare against running totals) -- flag[2] value once all of X_top is stored
   int64_t mu, nu;     // shape of the whole update (rows, uc) for diag_units_tile
 };
 
@@ -501,25 +519,48 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   const int nrows_cta = critical ? PCR : PR;
   const int64_t r0 = critical ? (int64_t)blockIdx.x * PCR : (int64_t)ncrit * PCR + (int64_t)(blockIdx.x - ncrit) * PR;
   const bool wact = w * 8 < nrows_cta;  // warps beyond the CTA's rows only help with the cooperative loads / emission
-  for (int e = tid; e < 4096; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    Ai[i * PLW + j] = dinv64[e];
-    Di[i * PLW + j] = dinv64[4096 + e];
-    Cs[i * PLW + j] = (64 + i < nb) ? Lblk[(int64_t)(64 + i) * ldl + j] : 0.0;
-  }
+  const int trace_id = fu.C ? 2 : 3;
+  if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 0);
   double* Bw = Bs + (w * 8) * PLB;  // this warp's 8 rows
-  if (wact) {
+  // Operands (A^-1, D^-1, C: 3 x 32 KB) and the CTA's rows (up to 64 KB) come in as 16-byte asynchronous copies, all in
+  // flight at once: one L2 round trip + the transfer (~1.7 us with every SM loading) instead of 16 dependent rounds of
+  // 8-byte loads (4.1 us of the 12.9 us panel, device timeline profiles/r2/trace_c2_phases.csv).
+  const bool async_ok = nb == NB && (ldb & 1) == 0 && (ldl & 1) == 0 && ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(Lblk) |
+                                                                           reinterpret_cast<uintptr_t>(dinv64)) & 15) == 0;
+  if (async_ok) {
+    for (int e = tid; e < 2048; e += 256) {  // 64 rows x 32 chunks of 2 doubles
+      const int i = e >> 5, j2 = (e & 31) * 2;
+      cp_async16(Ai + i * PLW + j2, dinv64 + i * 64 + j2, true);
+      cp_async16(Di + i * PLW + j2, dinv64 + 4096 + i * 64 + j2, true);
+      cp_async16(Cs + i * PLW + j2, Lblk + (int64_t)(64 + i) * ldl + j2, true);
+    }
+    for (int e = tid; e < nrows_cta * 64; e += 256) {  // rows x 64 chunks
+      const int rl = e >> 6, c2 = (e & 63) * 2;
+      const int64_t row = r0 + rl;
+      cp_async16(Bs + rl * PLB + c2, B + (row < rows ? row : 0) * ldb + c2, row < rows);
+    }
+    cp_async_wait_all();
+  } else {
+    for (int e = tid; e < 4096; e += 256) {
+      const int i = e >> 6, j = e & 63;
+      Ai[i * PLW + j] = dinv64[e];
+      Di[i * PLW + j] = dinv64[4096 + e];
+      Cs[i * PLW + j] = (64 + i < nb) ? Lblk[(int64_t)(64 + i) * ldl + j] : 0.0;
+    }
+    if (wact) {
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) {
-      const int64_t row = r0 + w * 8 + rr;
+      for (int rr = 0; rr < 8; ++rr) {
+        const int64_t row = r0 + w * 8 + rr;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = lane + 32 * cc;
-        Bw[rr * PLB + c] = (row < rows && c < nb) ? B[row * ldb + c] : 0.0;
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = lane + 32 * cc;
+          Bw[rr * PLB + c] = (row < rows && c < nb) ? B[row * ldb + c] : 0.0;
+        }
       }
     }
   }
   __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 10);  // operands + own rows staged
 
   double acc[8][2], af[16];
   if (wact) {
@@ -582,6 +623,7 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
     }
   }
   }  // wact
+  if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 11);  // solved rows stored
   // ---- fused K = nb update of the next block column: X_top published first (everybody needs it)
   if (fu.C) {
     const int ntop = ncrit;                  // CTAs that own rows of X_top
@@ -630,74 +672,102 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   // CTAs that hold rows of the next diagonal block update and publish them first (the next leaf is waiting for them) and
   // emit their planes afterwards; everybody else emits while waiting for X_top
   if (!critical) emit_planes();
-  if (!fu.C) return;
+  if (!fu.C) {
+    // rows below the square part (the (Y - m)^T rows that ride along): sliced here for the update that follows, with the
+    // scale of their maximum over its k-range -- everything left of this block is in global memory since earlier launches,
+    // this block's columns since the stores above.  (A slicing launch between this panel and the update costs ~6 us of
+    // the dependent chain, 31 times per evaluation at N = 8192.)
+    if (em.dyn_K > 0 && em.pl.planes && em.row_g0 + r0 + nrows_cta > em.pl.n_sq) {
+      __shared__ double wmax[8];
+      __syncthreads();
+      for (int rl = 0; rl < nrows_cta; ++rl) {
+        const int64_t row = r0 + rl, grow = em.row_g0 + row;
+        if (row >= rows || grow < em.pl.n_sq) continue;
+        tc_slice_row_cta(B + row * ldb + (em.dyn_k0 - em.col_g0), grow, em.dyn_k0, em.dyn_K, em.pl, wmax);
+      }
+    }
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_mark(trace_id, blockIdx.x == 0 ? 2 : 3);
+    return;
+  }
   // ---- C[own rows, 0:uc] -= X[own rows, 0:nb] X_top[0:uc, 0:nb]^T
   {
-    const int ntop = ncrit;
     double* Xt = Ai;  // [128][PLB] staged X_top: reuses the operand area (everybody passed the barrier above)
     if (tid == 0) {
       unsigned spins = 0;
-      while (atomicAdd(fu.flag + 2, 0) < ntop) {
+      while (atomicAdd(fu.flag + 2, 0) < fu.xtop_target) {
         __nanosleep(64);
         if (++spins > (1u << 24)) __trap();
       }
       __threadfence();
     }
     __syncthreads();
-    // (L2 loads: the rows were written by other CTAs of this grid)
+    if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 12);  // X_top complete (all critical CTAs stored)
+    // (L2 copies: the rows were written by other CTAs of this grid; cp.async.cg does not look in L1)
     if ((ldb & 1) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0) {
-      for (int e = tid; e < NB * 64; e += 256) {  // 128 rows x 64 double2
+      for (int e = tid; e < NB * 64; e += 256) {  // 128 rows x 64 chunks of 2 doubles
         const int i = e >> 6, c2 = (e & 63) * 2;
-        double2 v = make_double2(0.0, 0.0);
-        if (i < fu.uc) v = __ldcg(reinterpret_cast<const double2*>(B + (int64_t)i * ldb + c2));
-        *reinterpret_cast<double2*>(Xt + i * PLB + c2) = v;
+        cp_async16(Xt + i * PLB + c2, B + (int64_t)(i < fu.uc ? i : 0) * ldb + c2, i < fu.uc);
       }
+      cp_async_wait_all();
     } else {
       for (int e = tid; e < NB * NB; e += 256) {
         const int i = e >> 7, c = e & 127;
         Xt[i * PLB + c] = i < fu.uc ? __ldcg(B + (int64_t)i * ldb + c) : 0.0;
       }
     }
-    // accumulators = this warp's 8 rows of C (DMMA C-fragment layout: row g, columns 8 cb + 2q, +1)
-    const int64_t crow = r0 + w * 8 + g;
-    const bool rok = wact && crow < rows;
-    double cacc[16][2];
+    // accumulators = 8 rows of C (DMMA C-fragment layout: row g, columns 8 cb + 2q, +1).  Non-critical CTAs: warp w owns
+    // rows 8w.. and all 16 column blocks.  Critical CTAs (16 rows) spread the update over all 8 warps -- warp w takes rows
+    // 8 (w & 1).. and the 4 column blocks from 4 (w >> 1): 128 DMMAs per warp instead of 512 on two warps (the update was
+    // 6.9 us of the 19 us between the start of the kernel and the publish; profiles/r2/trace_c2_phases.csv).
+    auto update = [&](auto ncb_c, const int urow, const int cb0, const bool uact) {
+      constexpr int NCB = decltype(ncb_c)::value;
+      const double* Bu = Bs + urow * PLB;
+      const int64_t crow = r0 + urow + g;
+      const bool rok = uact && crow < rows;
+      double cacc[NCB][2];
 #pragma unroll
-    for (int cb = 0; cb < 16; ++cb) {
-      const int c = cb * 8 + 2 * q;
-      cacc[cb][0] = (rok && c < fu.uc) ? fu.C[crow * ldb + c] : 0.0;
-      cacc[cb][1] = (rok && c + 1 < fu.uc) ? fu.C[crow * ldb + c + 1] : 0.0;
-    }
-    __syncthreads();
-    if (wact) {
+      for (int cbi = 0; cbi < NCB; ++cbi) {
+        const int c = (cb0 + cbi) * 8 + 2 * q;
+        cacc[cbi][0] = (rok && c < fu.uc) ? fu.C[crow * ldb + c] : 0.0;
+        cacc[cbi][1] = (rok && c + 1 < fu.uc) ? fu.C[crow * ldb + c + 1] : 0.0;
+      }
+      __syncthreads();
+      if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 13);  // X_top staged, C fragments loaded
+      if (uact) {
 #pragma unroll 1
-      for (int kh = 0; kh < 2; ++kh) {  // two halves of k keep the A fragments at 16 registers
+        for (int kh = 0; kh < 2; ++kh) {  // two halves of k keep the A fragments at 16 registers
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) af[ks] = -Bw[g * PLB + kh * 64 + ks * 4 + q];
+          for (int ks = 0; ks < 16; ++ks) af[ks] = -Bu[g * PLB + kh * 64 + ks * 4 + q];
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
+          for (int ks = 0; ks < 16; ++ks)
 #pragma unroll
-          for (int cb = 0; cb < 16; ++cb) dmma884p(cacc[cb], af[ks], Xt[(cb * 8 + g) * PLB + kh * 64 + ks * 4 + q]);
+            for (int cbi = 0; cbi < NCB; ++cbi)
+              dmma884p(cacc[cbi], af[ks], Xt[((cb0 + cbi) * 8 + g) * PLB + kh * 64 + ks * 4 + q]);
+        }
       }
-    }
-    if (rok) {
+      if (rok) {
 #pragma unroll
-      for (int cb = 0; cb < 16; ++cb) {
-        const int c = cb * 8 + 2 * q;
-        if (c < fu.uc) fu.C[crow * ldb + c] = cacc[cb][0];
-        if (c + 1 < fu.uc) fu.C[crow * ldb + c + 1] = cacc[cb][1];
+        for (int cbi = 0; cbi < NCB; ++cbi) {
+          const int c = (cb0 + cbi) * 8 + 2 * q;
+          if (c < fu.uc) fu.C[crow * ldb + c] = cacc[cbi][0];
+          if (c + 1 < fu.uc) fu.C[crow * ldb + c + 1] = cacc[cbi][1];
+        }
       }
-    }
+    };
+    if (critical) update(std::integral_constant<int, 4>{}, (w & 1) * 8, (w >> 1) * 4, true);
+    else update(std::integral_constant<int, 16>{}, w * 8, 0, wact);
     // look-ahead: the critical CTAs hold the rows of the next diagonal block; the next leaf waits for all of them
     if (critical) {
       __syncthreads();
       if (tid == 0) {
         __threadfence();
         atomicAdd(fu.flag + 1, 1);
+        if (blockIdx.x == 0) trace_mark(trace_id, 1);  // first critical CTA published
       }
     }
   }
   if (critical) emit_planes();
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_mark(trace_id, blockIdx.x == 0 ? 2 : 3);
 }
 
 static size_t panel_smem_bytes(bool fused = false) {
@@ -760,7 +830,10 @@ struct LookAhead {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_inputs = nullptr, ev_side = nullptr, ev_u = nullptr;
   int* flag = nullptr;     // device counters (in the workspace): [0] head tiles done, [1] diagonal units done, [2] X_top CTAs
-  int target = 0;
+  int target = 0;          // value of flag[1] the next leaf waits for
+  int base1 = 0, base2 = 0;  // running totals of flag[1] / flag[2]: the counters are zeroed once per factorisation
+  int64_t follow_k0 = -1, follow_K = 0;  // the tcgen05 update that directly follows the block being factored (0: none)
+  int64_t dyn_k0 = -1, dyn_K = 0;        // k-range whose extra-row planes the last panel kernel has already written
   bool pending = false;
   bool enabled = false;
   bool slim = false;       // fp64, n > 128: slim leaves + potrf_panel_kernel (full block inverses filled in afterwards)
@@ -815,24 +888,28 @@ int lookahead_warm(cudaStream_t st) {
   return lookahead_init(la, &dummy, st);
 }
 
+// int32 accumulators: 128 * 128 * K * S < 2^31 (radix-256 digits; tests/test_digit_slicing_model.py); deeper updates use DMMA
+template <typename T>
+static bool tc_update_eligible(const LookAhead& la, int64_t m, int64_t n, int64_t K) {
+  return sizeof(T) == 8 && la.pl.planes && K >= tc_min_k() && K % 32 == 0 && n <= m && K * la.pl.S * 16384 < (1ll << 31);
+}
+
 template <typename T>
 static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, int64_t ldp, int64_t K, int64_t col0,
                            LookAhead& la, cudaStream_t st) {
   GemmOpts opts;
-  // int32 accumulators: 128 * 128 * K * S < 2^31 (radix-256 digits; tests/test_digit_slicing_model.py); deeper updates use DMMA
-  const bool use_tc = sizeof(T) == 8 && la.pl.planes && K >= tc_min_k() && K % 32 == 0 && n <= m &&
-                      K * la.pl.S * 16384 < (1ll << 31);
+  const bool use_tc = tc_update_eligible<T>(la, m, n, K);
   if (use_tc) {
     // operand rows without a static scale: the extra rows below the square part (or every row, GPK_TC_STATIC=0)
     const int64_t r0 = col0 + K;
     const int64_t dyn0 = la.pl.is_static ? (la.pl.n_sq > r0 ? la.pl.n_sq : r0) : r0;
-    if (dyn0 < r0 + m)
+    if (dyn0 < r0 + m && !(la.pl.is_static && la.dyn_k0 == col0 && la.dyn_K == K))  // (else: the last panel kernel did it)
       GPK_TRY(tc_slice_rows((const double*)P + (dyn0 - r0) * ldp, ldp, dyn0, r0 + m - dyn0, col0, K, la.pl, st));
   }
   if (la.enabled) {
-    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));
     opts.head_flag = la.flag;
-    la.target = diag_units_total(m, n);  // 32x32 units of the next 128x128 diagonal block
+    la.base1 += diag_units_total(m, n);  // 32x32 units of the next 128x128 diagonal block
+    la.target = la.base1;
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
     la.pending = true;
   }
@@ -906,8 +983,10 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
       const int64_t crit_rows = fuse_cols < rows - n ? fuse_cols : rows - n;   // rows of the next diagonal block
       fu.ncrit = (int)((crit_rows + PCR - 1) / PCR);
     }
-    GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));
-    la.target = fu.ncrit;  // every critical CTA reports once
+    la.base1 += fu.ncrit;  // every critical CTA reports once
+    la.base2 += fu.ncrit;  // ... and counts itself into flag[2] when its rows of X_top are stored
+    la.target = la.base1;
+    fu.xtop_target = la.base2;
     GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
     la.pending = true;
     {
@@ -923,6 +1002,12 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
     return 0;
   }
   if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
+  la.dyn_K = 0;
+  if (la.slim && em.pl.planes && n == NB && la.follow_K > 0 && la.follow_k0 + la.follow_K == col0 + n && rows > la.pl.n_sq - col0) {
+    // the tcgen05 update of [follow_k0, follow_k0 + follow_K) is the next launch: this panel also slices the extra rows for it
+    em.dyn_k0 = la.dyn_k0 = la.follow_k0;
+    em.dyn_K = la.dyn_K = la.follow_K;
+  }
   if (la.slim) {
     ProfScope ps(PROF_PANEL, ls, (double)(rows - n) * n * 0.5 * n);
     const unsigned nblk = (unsigned)((rows - n + PR - 1) / PR);
@@ -940,19 +1025,27 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   return 0;
 }
 
+// (fk0, fK): the k-range of the trailing update that directly follows this sub-factorisation when it runs on tcgen05
+// (fK = 0: none) -- the last panel kernel before it prepares the extra rows' digit planes (potrf_block)
 template <typename T>
 static int potrf_rec(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, int64_t col0, LookAhead& la,
-                     cudaStream_t st) {
-  if (n <= NB) return potrf_block<T>(A, n, rows, lda, info, dinv, col0, 0, la, st);
+                     cudaStream_t st, int64_t fk0 = -1, int64_t fK = 0) {
+  if (n <= NB) {
+    la.follow_k0 = fk0;
+    la.follow_K = fK;
+    return potrf_block<T>(A, n, rows, lda, info, dinv, col0, 0, la, st);
+  }
   const int64_t n1 = split_point(n);
   if (n <= 2 * NB && la.fuse) {  // two diagonal blocks: the K = 128 update between them is fused into the first panel
+    la.follow_K = 0;
     GPK_TRY(potrf_block<T>(A, n1, rows, lda, info, dinv, col0, (int)(n - n1), la, st));
-    return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st);
+    return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st, fk0, fK);
   }
-  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, la, st));
+  const bool tc = tc_update_eligible<T>(la, rows - n1, n - n1, n1);
+  GPK_TRY(potrf_rec<T>(A, n1, rows, lda, info, dinv, col0, la, st, col0, tc ? n1 : 0));
   // trailing update: A[n1:rows, n1:n] -= A[n1:rows, :n1] A[n1:n, :n1]^T  (lower tiles only)
   GPK_TRY(trailing_update<T>(A + n1 * lda + n1, lda, rows - n1, n - n1, A + n1 * lda, lda, n1, col0, la, st));
-  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st);
+  return potrf_rec<T>(A + n1 * lda + n1, n - n1, rows - n1, lda, info, dinv, col0 + n1, la, st, fk0, fK);
 }
 
 static bool slim_enabled() {
@@ -986,6 +1079,7 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   // the look-ahead counter lives in the last 256 bytes of the dinv area's alignment slack (see potrf_ws_bytes)
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(dinv) + (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(T));
   if (n > NB) GPK_TRY(lookahead_init(la, flag, st));
+  if (la.enabled) GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));  // counters run up from here (la.base1 / base2)
   la.slim = sizeof(T) == 8 && n > NB && slim_enabled();
   la.fuse = la.slim && la.enabled && fuse_enabled();
   // digit-plane store for the tcgen05 trailing updates: fp64, slim panels (they emit the planes), n >= 2 tc_min_k
@@ -1059,6 +1153,11 @@ int trsm_t(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t nrhs, in
 }
 
 // phase timing of one leaf launch (clock64 at phase boundaries), for tuning
+int trace_set_potrf(TraceBuf tb) {
+  GPK_CUDA_OK(cudaMemcpyToSymbol(g_trace, &tb, sizeof(tb)));
+  return 0;
+}
+
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
   GPK_TRY(leaf_attr<double>());
   potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0, 0);

@@ -314,6 +314,11 @@ GPK_API void gpk_launch_count_reset(void);
 /* Tuning aid: runs ONE fp64 128x128 leaf (factor+invert) and stores clock64() at its phase
  * boundaries into dbg[0..9] (device int64). */
 GPK_API int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* stream);
+/* Tuning aid: device timeline of a factorisation.  While `buf` is set, thread 0 of selected CTAs of the leaf (id 1), fused
+ * panel (2), plain panel (3) and tcgen05 update (4) kernels append (%globaltimer ns, id << 8 | phase) pairs to buf[2 * capacity]
+ * (device uint64) through the counter *pos (device uint32).  phase 0 = first CTA started, 1 = inputs ready (leaf) / look-ahead
+ * block published (panel, update), 2 = first CTA done, 3 = last CTA done.  buf = NULL switches it off.  scripts/trace_chain.py. */
+GPK_API int gpk_debug_trace(void* buf, void* pos, unsigned int capacity);
 GPK_API int gpk_prof_enable(int on);
 GPK_API int gpk_prof_read(double* ms, int64_t* launches, int n);
 GPK_API int gpk_prof_read2(double* ms, int64_t* launches, double* work, int n);
