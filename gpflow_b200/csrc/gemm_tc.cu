@@ -320,44 +320,54 @@ syrk_i8_kernel(TcPlanes pl, int64_t rb0, int64_t kb0, double* __restrict__ C, in
       if (tr0) trace_mark(4, 13);  // accumulators complete
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        double acc[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.0;
-        double w = 1.0;
-        for (int g = 0; g < NACC; ++g) {
-          uint32_t v[32];
-          tc_ld32(lane_addr + (uint32_t)(g * TC_BN + half * 32), v);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fma(tc_int_to_double((int)v[c]), w, acc[c]);
-          w *= 0.00390625;  // 2^-8 (radix 256)
-        }
-        if (half == 1) {  // accumulators drained: the MMA warp may start the next tile
-          tc_fence_before();
-          mbar_arrive(tempty);
-        }
-        if (tr0) trace_mark(4, 14 + 2 * half);  // TMEM drained + converted (14 / 16)
         const double* sc = rowscale + colb + half * 32;
-        if (fullw) {
-          // the bulk reduction issued from this row two halves ago has finished READING the staging row
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // the bulk reduction issued from this row one half ago has finished READING the staging row
+        if (fullw) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #pragma unroll
-          for (int c2 = 0; c2 < 16; ++c2) {
-            const double2 s2 = __ldg(reinterpret_cast<const double2*>(sc + 2 * c2));
-            double2 o;
-            o.x = (rs * s2.x) * acc[2 * c2];
-            o.y = (rs * s2.y) * acc[2 * c2 + 1];
-            *reinterpret_cast<double2*>(srow + 2 * c2) = o;
+        for (int qq = 0; qq < 2; ++qq) {  // 16 columns at a time: all NACC accumulator reads in flight, one wait
+          uint32_t v[NACC][16];
+#pragma unroll
+          for (int g = 0; g < NACC; ++g) tc_ld16_nowait(lane_addr + (uint32_t)(g * TC_BN + half * 32 + qq * 16), v[g]);
+          tc_ld_wait();
+          if (half == 1 && qq == 1) {  // accumulators drained: the MMA warp may start the next tile
+            tc_fence_before();
+            mbar_arrive(tempty);
           }
+          double acc[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+          double w = 1.0;
+#pragma unroll
+          for (int g = 0; g < NACC; ++g) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = fma(tc_int_to_double((int)v[g][c]), w, acc[c]);
+            w *= 0.00390625;  // 2^-8 (radix 256)
+          }
+          if (fullw) {
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+              const double2 s2 = __ldg(reinterpret_cast<const double2*>(sc + qq * 16 + 2 * c2));
+              double2 o;
+              o.x = (rs * s2.x) * acc[2 * c2];
+              o.y = (rs * s2.y) * acc[2 * c2 + 1];
+              *reinterpret_cast<double2*>(srow + qq * 16 + 2 * c2) = o;
+            }
+          } else if (live) {  // ragged right edge / unaligned C: element-wise read-modify-write (rare)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {  // (fully unrolled: a runtime index would move acc[] to local memory)
+              const int cc = half * 32 + qq * 16 + c;
+              if (colb + cc < n) crow[cc] = fma(rs * __ldg(sc + qq * 16 + c), acc[c], crow[cc]);
+            }
+          }
+        }
+        if (tr0) trace_mark(4, 14 + 2 * half);  // TMEM drained + converted + staged (14 / 16)
+        if (fullw) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (live)
             asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 256;" ::"l"(crow + half * 32),
                          "r"(srow_s)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        } else if (live) {  // ragged right edge / unaligned C: element-wise read-modify-write (rare)
-#pragma unroll
-          for (int c = 0; c < 32; ++c)  // (fully unrolled: a runtime index would move acc[] to local memory)
-            if (colb + half * 32 + c < n) crow[half * 32 + c] = fma(rs * __ldg(sc + c), acc[c], crow[half * 32 + c]);
         }
         if (tr0) trace_mark(4, 15 + 2 * half);  // update issued (15 / 17)
       }

@@ -332,7 +332,7 @@ __device__ __forceinline__ void write_dinv64(const T* S, T* __restrict__ dinv) {
 template <typename T, bool SLIM>
 __global__ void __launch_bounds__(256, 1)
 potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, int32_t* info, int info_base,
-                  long long* dbg, int* wait_flag, int wait_target, int64_t batch_stride) {
+                  long long* dbg, int* wait_flag, int wait_target, int64_t batch_stride, int* done_flag) {
   // grid > 1: a BATCH of independent blocks (gpk_potrf_batched, n <= 128), block b at A + b * batch_stride with its own
   // inverse slot and info word
   A += (int64_t)blockIdx.x * batch_stride;
@@ -460,6 +460,10 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
   if (SLIM) write_dinv64<T>(S, dinv); else write_dinv<T>(S, dinv);
   __syncthreads();
   GPK_DBG(9);
+  if (done_flag && tid == 0) {  // (after the barrier above: L and the inverses of every thread are stored) the panel kernel
+    __threadfence();            // below this block is already resident and polls this counter instead of waiting for a launch
+    atomicAdd(done_flag, 1);
+  }
   if (tid == 0 && blockIdx.x == 0) trace_mark(1, 2);
 #undef GPK_DBG
 }
@@ -491,6 +495,8 @@ struct PanelEmit {
   int64_t col_g0;     // global column index of the block
   int64_t dyn_k0;     // dyn_K > 0: the tcgen05 update of the k-range [dyn_k0, dyn_k0 + dyn_K) follows this panel (it ends at
   int64_t dyn_K;      // this block); the CTAs that own rows below the square part slice them for it (dynamic scales)
+  int* leaf_flag;     // not nullptr: the leaf of this block runs CONCURRENTLY (other stream); its outputs (Lblk, dinv64) are
+  int leaf_target;    // valid once *leaf_flag >= leaf_target.  The CTA's own rows are fetched before the wait.
 };
 constexpr int PCR = 16;  // rows per CRITICAL CTA of the fused panel (see the row mapping in the kernel)
 struct PanelFuse {
@@ -527,25 +533,39 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   // 8-byte loads (4.1 us of the 12.9 us panel, device timeline profiles/r2/trace_c2_phases.csv).
   const bool async_ok = nb == NB && (ldb & 1) == 0 && (ldl & 1) == 0 && ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(Lblk) |
                                                                            reinterpret_cast<uintptr_t>(dinv64)) & 15) == 0;
+  auto wait_leaf = [&]() {  // flag hop instead of a launch boundary between the leaf and this kernel (~3.5 us of the chain)
+    if (!em.leaf_flag) return;
+    if (tid == 0) {
+      unsigned spins = 0;
+      while (atomicAdd(em.leaf_flag, 0) < em.leaf_target) {
+        __nanosleep(32);
+        if (++spins > (1u << 25)) __trap();
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  };
   if (async_ok) {
+    for (int e = tid; e < nrows_cta * 64; e += 256) {  // rows x 64 chunks (independent of the leaf: issued first)
+      const int rl = e >> 6, c2 = (e & 63) * 2;
+      const int64_t row = r0 + rl;
+      cp_async16(Bs + rl * PLB + c2, B + (row < rows ? row : 0) * ldb + c2, row < rows);
+    }
+    wait_leaf();
     for (int e = tid; e < 2048; e += 256) {  // 64 rows x 32 chunks of 2 doubles
       const int i = e >> 5, j2 = (e & 31) * 2;
       cp_async16(Ai + i * PLW + j2, dinv64 + i * 64 + j2, true);
       cp_async16(Di + i * PLW + j2, dinv64 + 4096 + i * 64 + j2, true);
       cp_async16(Cs + i * PLW + j2, Lblk + (int64_t)(64 + i) * ldl + j2, true);
     }
-    for (int e = tid; e < nrows_cta * 64; e += 256) {  // rows x 64 chunks
-      const int rl = e >> 6, c2 = (e & 63) * 2;
-      const int64_t row = r0 + rl;
-      cp_async16(Bs + rl * PLB + c2, B + (row < rows ? row : 0) * ldb + c2, row < rows);
-    }
     cp_async_wait_all();
   } else {
+    wait_leaf();
     for (int e = tid; e < 4096; e += 256) {
       const int i = e >> 6, j = e & 63;
-      Ai[i * PLW + j] = dinv64[e];
-      Di[i * PLW + j] = dinv64[4096 + e];
-      Cs[i * PLW + j] = (64 + i < nb) ? Lblk[(int64_t)(64 + i) * ldl + j] : 0.0;
+      Ai[i * PLW + j] = __ldcg(dinv64 + e);
+      Di[i * PLW + j] = __ldcg(dinv64 + 4096 + e);
+      Cs[i * PLW + j] = (64 + i < nb) ? __ldcg(Lblk + (int64_t)(64 + i) * ldl + j) : 0.0;
     }
     if (wact) {
 #pragma unroll
@@ -835,6 +855,9 @@ struct LookAhead {
   int64_t follow_k0 = -1, follow_K = 0;  // the tcgen05 update that directly follows the block being factored (0: none)
   int64_t dyn_k0 = -1, dyn_K = 0;        // k-range whose extra-row planes the last panel kernel has already written
   bool pending = false;
+  bool flaghop = false;    // slim + look-ahead: leaves alone on the side stream, panels / updates on the main stream; a panel
+  bool side_started = false;  // kernel waits for its leaf through flag[3] (leaves_done) instead of a cross-stream event
+  int leaves_done = 0;
   bool enabled = false;
   bool slim = false;       // fp64, n > 128: slim leaves + potrf_panel_kernel (full block inverses filled in afterwards)
   bool fuse = false;       // slim + look-ahead: the K = 128 updates are applied by the panel kernel itself
@@ -844,6 +867,23 @@ struct LookAhead {
 static bool lookahead_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPK_LOOKAHEAD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static bool flaghop_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_FLAG_HOPS"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -910,7 +950,7 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
     opts.head_flag = la.flag;
     la.base1 += diag_units_total(m, n);  // 32x32 units of the next 128x128 diagonal block
     la.target = la.base1;
-    GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
+    if (!la.flaghop) GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));  // everything the next leaf needs except U itself
     la.pending = true;
   }
   int rc;
@@ -918,7 +958,7 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
     rc = syrk_tc_planes((double*)C, ldc, m, n, la.pl, col0 + K, col0, K, 1, st, &opts);
   else
     rc = gemm_t<T>(0, 1, m, n, K, T(-1), P, ldp, P, ldp, T(1), C, ldc, GPK_GEMM_LOWER_ONLY, st, &opts);
-  if (rc == 0 && la.enabled) GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));  // U complete
+  if (rc == 0 && la.enabled && !la.flaghop) GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));  // U complete
   return rc;
 }
 
@@ -937,7 +977,22 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   cudaStream_t ls = st;
   int* wf = nullptr;
   int wt = 0;
-  if (la.pending) {
+  int* done = nullptr;
+  if (la.flaghop) {
+    // Flag hops: every leaf runs on the side stream (one after the other), every panel / update on the main stream.  The leaf
+    // waits for its diagonal block through flag[1] (published by the update or the fused panel before it), the panel below
+    // it waits for the leaf through flag[3]; neither needs a launch boundary or a cross-stream event in between.
+    if (!la.side_started) {  // the first leaf: its inputs are whatever precedes the factorisation on the caller's stream
+      GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
+      GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_inputs, 0));
+      la.side_started = true;
+    }
+    ls = la.side;
+    if (la.pending) { wf = la.flag + 1; wt = la.target; }
+    done = la.flag + 3;
+    la.leaves_done += 1;
+    la.pending = false;
+  } else if (la.pending) {
     GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_inputs, 0));
     ls = la.side;
     wf = la.flag + 1;  // the leaf needs only the diagonal block of U's output
@@ -946,9 +1001,9 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   {
     ProfScope ps(PROF_LEAF, ls);
     if (la.slim)
-      potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0);
+      potrf_leaf_kernel<T, true><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0, done);
     else
-      potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0);
+      potrf_leaf_kernel<T, false><<<1, 256, leaf_smem_bytes<T>(), ls>>>(A, lda, (int)n, dblk, info, (int)col0, nullptr, wf, wt, 0, done);
     GPK_LAUNCH_OK();
   }
   if (rows <= n) {
@@ -965,6 +1020,20 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
     em.pl = la.pl;
     em.row_g0 = col0 + n;
     em.col_g0 = col0;
+  }
+  if (la.flaghop) {
+    // The panel CTAs (one per SM: shared memory) spin until the leaf has finished, so the leaf must be able to get an SM
+    // whatever the block scheduler does first: only grids that leave two SMs free may poll; a larger grid (N > ~9000) is
+    // ordered behind the leaf by an event, as a launch boundary would.
+    const int64_t prow = rows - n;
+    const int64_t ctas = fuse_cols > 0 ? (fuse_cols + PCR - 1) / PCR + (prow + PR - 1) / PR : (prow + PR - 1) / PR;
+    if (ctas <= num_sms() - 2) {
+      em.leaf_flag = la.flag + 3;
+      em.leaf_target = la.leaves_done;
+    } else {
+      GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
+      GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));
+    }
   }
   if (la.slim && fuse_cols > 0) {
     // The fused panel + update plays the role of U: it runs on the MAIN stream (behind the previous U, which it needs
@@ -987,7 +1056,7 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
     la.base2 += fu.ncrit;  // ... and counts itself into flag[2] when its rows of X_top are stored
     la.target = la.base1;
     fu.xtop_target = la.base2;
-    GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
+    if (!la.flaghop) GPK_CUDA_OK(cudaEventRecord(la.ev_inputs, st));
     la.pending = true;
     {
       // work: MACs of the solve (half of rows x 128 x 128: triangular) + the fused K = 128 update
@@ -998,10 +1067,11 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
                                                                      (int)n, (const double*)dblk, em, fu);
       GPK_LAUNCH_OK();
     }
-    GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));
+    if (!la.flaghop) GPK_CUDA_OK(cudaEventRecord(la.ev_u, st));
     return 0;
   }
-  if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
+  if (la.flaghop) ls = st;  // the panel runs on the main stream (behind the fused panel / update it needs completely)
+  else if (la.pending) GPK_CUDA_OK(cudaStreamWaitEvent(la.side, la.ev_u, 0));  // the panel below needs all of U
   la.dyn_K = 0;
   if (la.slim && em.pl.planes && n == NB && la.follow_K > 0 && la.follow_k0 + la.follow_K == col0 + n && rows > la.pl.n_sq - col0) {
     // the tcgen05 update of [follow_k0, follow_k0 + follow_K) is the next launch: this panel also slices the extra rows for it
@@ -1082,6 +1152,7 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   if (la.enabled) GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));  // counters run up from here (la.base1 / base2)
   la.slim = sizeof(T) == 8 && n > NB && slim_enabled();
   la.fuse = la.slim && la.enabled && fuse_enabled();
+  la.flaghop = la.slim && la.enabled && flaghop_enabled();
   // digit-plane store for the tcgen05 trailing updates: fp64, slim panels (they emit the planes), n >= 2 tc_min_k
   const int S = pick_slices(cond_hint);
   if (sizeof(T) == 8) g_last_slices = 0;
@@ -1091,6 +1162,10 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
     if (la.pl.is_static) GPK_TRY(tc_row_exponents((const double*)A, lda, la.pl, st));  // from the ORIGINAL diagonal
   }
   GPK_TRY(potrf_rec<T>(A, n, rows, lda, info, dinv, 0, la, st));
+  if (la.flaghop && la.side_started) {  // the caller's stream continues behind the last leaf
+    GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
+    GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));
+  }
   // slim leaves left only the 64x64 diagonal inverses: the full 128x128 block inverses that gpk_trsm consumes are
   // computed now, all blocks in parallel, off the factorisation's critical path (skipped when nobody will use them)
   if (la.slim && need_dinv) GPK_TRY(trtri_diag_t<T>(A, n, lda, dinv, st));
@@ -1106,7 +1181,7 @@ int potrf_batched_small_t(T* A, int64_t n, int64_t lda, int64_t stride, int batc
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, (size_t)batch * sizeof(int32_t), st));
   ProfScope ps(PROF_LEAF, st);
   potrf_leaf_kernel<T, false><<<(unsigned)batch, 256, leaf_smem_bytes<T>(), st>>>(A, lda, (int)n, dinv, info, 0, nullptr, nullptr,
-                                                                                  0, stride);
+                                                                                  0, stride, nullptr);
   GPK_LAUNCH_OK();
   return 0;
 }
@@ -1160,7 +1235,7 @@ int trace_set_potrf(TraceBuf tb) {
 
 int leaf_debug(double* A, int64_t lda, int n, double* dinv, long long* dbg, cudaStream_t st) {
   GPK_TRY(leaf_attr<double>());
-  potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0, 0);
+  potrf_leaf_kernel<double, false><<<1, 256, leaf_smem_bytes<double>(), st>>>(A, lda, n, dinv, nullptr, 0, dbg, nullptr, 0, 0, nullptr);
   GPK_LAUNCH_OK();
   return 0;
 }

@@ -174,6 +174,24 @@ def test_potrf_extra_rows_give_solves(cuda_device):
     assert np.all(np.triu(got[:n], 1)[:128, 128:] == 123.0)  # strict upper tiles untouched
 
 
+def test_potrf_panel_grid_larger_than_the_gpu(cuda_device):
+    """n = 9856: the panel kernels below the first diagonal blocks have more CTAs than the GPU has SMs.  Those launches are
+    ordered behind their leaf by an event; smaller grids poll the leaf's completion counter (a grid that fills every SM
+    with polling CTAs would lock the leaf out -- potrf.cu::potrf_block).  The factor is checked through L L^T = A on a
+    sample of rows and through log det against LAPACK."""
+    rng = np.random.default_rng(12)
+    n = 9856
+    B = rng.standard_normal((n, 64))
+    d = 1.0 + rng.uniform(0, 1, n)
+    K = B @ B.T / 64 + np.diag(d)
+    L, _ = ops.cholesky(ops.to_device(K))
+    Ln = to_np(L)
+    rows = rng.choice(n, 40, replace=False)
+    assert_allclose(Ln[rows] @ Ln.T, K[rows], rtol=0, atol=2e-10)
+    sign, logdet = np.linalg.slogdet(K)
+    assert_allclose(2.0 * np.log(np.diag(Ln)).sum(), logdet, rtol=1e-11)
+
+
 def test_potrf_reports_non_positive_definite(cuda_device):
     rng = np.random.default_rng(10)
     n = 200
