@@ -55,16 +55,91 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {  // 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// ---- one 32x32 block pair of the in-leaf trailing update: C[R0.., C0..] -= S[R0.., jb:jb+32] S[C0.., jb:jb+32]^T (c <= r) -------
+// 64 threads (sub = 0..63) per pair.  fp64: two warps x (2 m-blocks x 4 n-blocks) of mma.sync.m8n8k4.f64 -- 48 shared loads +
+// 64 DMMAs per warp instead of 256 loads + 512 DFMAs of the 4x4 micro-tile form (4.3k -> cycles measured on the pair that
+// gates the next diagonal block, scripts/leaf_timing.py).  fp32: 8 x 8 threads, interleaved 4x4 micro-tiles.
+// one 16-row half (wv = 0, 1) of a pair by ONE warp
+__device__ __forceinline__ void leaf_pair_half(double* S, int R0, int C0, int jb, int wv, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  double acc[2][4][2];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  // k-step ks covers k = ks, ks + 8, ks + 16, ks + 24 (lane q supplies k = ks + 8 q): with the odd row stride the 32 lanes of a
+  // fragment load then touch every 8-byte bank exactly twice (2 wavefronts, the minimum for 256 bytes) instead of up to 4
+  // times with k = 4 ks + q -- the shared-memory pipe also carries the shuffles of the concurrent 32x32 factorisation
+  const double* Ra = S + (R0 + 16 * wv + g) * LS + jb + 8 * q;
+  const double* Rb = S + (C0 + g) * LS + jb + 8 * q;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    double a[2], b[4];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) a[mb] = Ra[mb * 8 * LS + ks];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) b[nb] = Rb[nb * 8 * LS + ks];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) dmma884p(acc[mb][nb], a[mb], b[nb]);
+  }
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int r = R0 + 16 * wv + 8 * mb + g, c = C0 + 8 * nb + 2 * q;
+      if (c <= r) S[r * LS + c] -= acc[mb][nb][0];
+      if (c + 1 <= r) S[r * LS + c + 1] -= acc[mb][nb][1];
+    }
+}
+__device__ __forceinline__ void leaf_pair_update(double* S, int R0, int C0, int jb, int sub) {
+  leaf_pair_half(S, R0, C0, jb, sub >> 5, sub & 31);
+}
+// the pair that IS the next diagonal block (R0 = C0 = t0), spread over all 8 warps: warp w takes the 8-row block w >> 1 and the
+// two 8-column blocks 2 (w & 1), +1 (those not above the diagonal): 16 DMMAs per warp, then everybody meets at a barrier and
+// warp 0 factors the block while the others apply the rest of the update
+__device__ __forceinline__ void leaf_pair0_all(double* S, int t0, int jb, int w, int lane) {
+  const int g = lane >> 2, q = lane & 3, mb = w >> 1, nb0 = 2 * (w & 1);
+  if (nb0 > mb) return;  // both column blocks above the diagonal
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const double* Ra = S + (t0 + 8 * mb + g) * LS + jb + 8 * q;  // (k = ks + 8 q, see leaf_pair_half)
+  const double* Rb = S + (t0 + 8 * nb0 + g) * LS + jb + 8 * q;
+  const bool second = nb0 + 1 <= mb;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const double a = Ra[ks];
+    dmma884p(acc[0], a, Rb[ks]);
+    if (second) dmma884p(acc[1], a, Rb[8 * LS + ks]);
+  }
+  const int r = t0 + 8 * mb + g;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = t0 + 8 * (nb0 + j) + 2 * q;
+    if (j == 1 && !second) break;
+    if (c <= r) S[r * LS + c] -= acc[j][0];
+    if (c + 1 <= r) S[r * LS + c + 1] -= acc[j][1];
+  }
+}
+
 template <typename T> __device__ __forceinline__ T rsqrt_t(T x);
-// fp32 MUFU.RSQ seed + two Newton steps in fp64 (relative error ~2^-52): ~2/3 of the latency of the
-// library rsqrt(), which sits on the serial pivot chain of the diagonal-block factorisation.
+// MUFU.RSQ64H seed (rsqrt.approx.f64: ~2^-22 relative, no fp64 <-> fp32 conversions) + ONE third-order step
+// y1 = y0 (1 + e/2 + 3 e^2/8), e = 1 - x y0^2: error ~ e^3 = 2^-66 before rounding.  Four dependent fp64 operations
+// instead of the six of two Newton steps -- this sits on the serial pivot chain of the diagonal-block factorisation.
 template <> __device__ __forceinline__ double rsqrt_t<double>(double x) {
-  double y = (double)rsqrtf((float)x);
-  double e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-x * y, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  return y;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double q = y * e;
+  return fma(q, p, y);
 }
 template <> __device__ __forceinline__ float rsqrt_t<float>(float x) { return rsqrtf(x); }
 
@@ -221,6 +296,96 @@ __device__ __forceinline__ void mt_zero(T (&acc)[4][4]) {
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
 }
 
+__device__ __forceinline__ void leaf_pair_update(float* S, int R0, int C0, int jb, int sub) {
+  const int ptr_ = sub >> 3, ptc = sub & 7;
+  float acc[4][4];
+  mt_zero(acc);
+  const float* Ra = S + (R0 + ptr_) * LS + jb;
+  const float* Rb = S + (C0 + ptc) * LS + jb;
+  mt_acc<float>(acc, 0, 32,
+                [&](int i, int k) { return Ra[i * 8 * LS + k]; },
+                [&](int j, int k) { return Rb[j * 8 * LS + k]; });
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = R0 + ptr_ + 8 * i, c = C0 + ptc + 8 * j;
+      if (c <= r) S[r * LS + c] -= acc[i][j];
+    }
+}
+
+// level 32 of the inverse on DMMA (fp64): X = -Linv_II (L_IJ Linv_JJ) for the pairs (I,J) = (1,0), (3,2); warps 0-1 / 2-3 take
+// one pair each (16 rows x 32 columns per warp), the rest of the CTA only joins the barriers.  Storage conventions as in
+// invert_offdiag_128 below (Linv transposed in the upper triangle of S, diagonal included).
+__device__ __forceinline__ void invert_level32_dmma(double* S, double* tmp) {
+  const int tid = threadIdx.x, pair = tid >> 6, wv = (tid >> 5) & 1, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int J = 2 * pair, I = J + 1;
+  double acc[2][4][2];
+  if (pair < 2) {  // T = L_IJ Linv_JJ;  Linv_JJ[k][c] = S[J*32+c][J*32+k] for k >= c
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    const double* La = S + (I * 32 + 16 * wv + g) * LS + J * 32 + q;
+    const double* Lb = S + (J * 32 + g) * LS + J * 32 + q;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      double a[2], b[4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) a[mb] = La[mb * 8 * LS + 4 * ks];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const double v = Lb[nb * 8 * LS + 4 * ks];
+        b[nb] = (4 * ks + q >= 8 * nb + g) ? v : 0.0;
+      }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          if (4 * ks + 3 >= 8 * nb) dmma884p(acc[mb][nb], a[mb], b[nb]);  // (k-steps entirely above the diagonal are zero)
+    }
+    double* tp = tmp + pair * 1024;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        *reinterpret_cast<double2*>(tp + (16 * wv + 8 * mb + g) * 32 + 8 * nb + 2 * q) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+  }
+  __syncthreads();
+  if (pair < 2) {  // X = -Linv_II T;  Linv_II[r][k] = S[I*32+k][I*32+r] for r >= k;  stored transposed: S[J*32+c][I*32+r]
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    const double* tp = tmp + pair * 1024;
+    const double* Li = S + (I * 32 + q) * LS + I * 32 + 16 * wv + g;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      double a[2], b[4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const double v = Li[4 * ks * LS + 8 * mb];
+        a[mb] = (16 * wv + 8 * mb + g >= 4 * ks + q) ? v : 0.0;
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) b[nb] = tp[(4 * ks + q) * 32 + 8 * nb + g];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884p(acc[mb][nb], a[mb], b[nb]);
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int r = 16 * wv + 8 * mb + g, c = 8 * nb + 2 * q;
+        S[(J * 32 + c) * LS + I * 32 + r] = -acc[mb][nb][0];
+        S[(J * 32 + c + 1) * LS + I * 32 + r] = -acc[mb][nb][1];
+      }
+  }
+  __syncthreads();
+}
+
 // ---- off-diagonal blocks of the inverse (diagonal 32x32 blocks already inverted) ---------------------
 // Linv is stored TRANSPOSED in the upper triangle of S INCLUDING the diagonal: Linv[r][c] = S[c][r],
 // r >= c.  The strict lower triangle of S still holds L.  tmp: 4096-element scratch.
@@ -231,7 +396,9 @@ template <typename T>
 __device__ void invert_offdiag_128(T* S, T* tmp, bool level64 = true) {
   const int tid = threadIdx.x;
   T acc[4][4];
-  {  // ---- level 32: pairs (I,J) = (1,0) and (3,2)
+  if (sizeof(T) == 8) {  // ---- level 32 on DMMA: pairs (I,J) = (1,0) and (3,2), two warps per pair
+    invert_level32_dmma(reinterpret_cast<double*>(S), reinterpret_cast<double*>(tmp));
+  } else {  // ---- level 32: pairs (I,J) = (1,0) and (3,2)
     const int pair = tid >> 6, sub = tid & 63, tr = sub >> 3, tc = sub & 7;
     const int J = 2 * pair, I = J + 1;
     if (pair < 2) {
@@ -395,38 +562,47 @@ potrf_leaf_kernel(T* __restrict__ A, int64_t lda, int n, T* __restrict__ dinv, i
       }
       __syncthreads();
       if (J == 0) GPK_DBG(4);
-      // trailing update by 32x32 block pairs (rb >= cb), 64 threads (8x8 interleaved 4x4 micro-tiles) per pair:
-      //   C[r][c] -= sum_k S[r][jb+k] S[c][jb+k];   pair 0 = the next diagonal block, done by warps 0-1 only
+      // trailing update by 32x32 block pairs (rb >= cb):  C[r][c] -= sum_k S[r][jb+k] S[c][jb+k]
       const int nblk = nr / 32, npairs = nblk * (nblk + 1) / 2;
-      const int sub = tid & 63, ptr_ = sub >> 3, ptc = sub & 7;
-      int pr = grp;
-      while (pr < npairs) {
-        int rbk = 0, rem = pr;
-        while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
-        const int cbk = rem;
-        const int R0 = t0 + rbk * 32, C0 = t0 + cbk * 32;
-        T acc[4][4];
-        mt_zero(acc);
-        const T* Ra = S + (R0 + ptr_) * LS + jb;
-        const T* Rb = S + (C0 + ptc) * LS + jb;
-        mt_acc<T>(acc, 0, 32,
-                  [&](int i, int k) { return Ra[i * 8 * LS + k]; },
-                  [&](int j, int k) { return Rb[j * 8 * LS + k]; });
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = R0 + ptr_ + 8 * i, c = C0 + ptc + 8 * j;
-            if (c <= r) S[r * LS + c] -= acc[i][j];
+      if (sizeof(T) == 8) {
+        // fp64 (DMMA): pair 0 = the next diagonal block by ALL warps (0.6k cycles instead of 3.6k on two warps that share
+        // their DP pipes with the rest), barrier, then warp 0 factors it while warps 1-3 and 5-7 apply the other pairs in
+        // 16-row halves; warp 4 shares warp 0's scheduler and stays idle (the concurrent update slowed the 32x32
+        // factorisation from 8.6k to 10.6k cycles: scripts/leaf_timing.py)
+        const int w8 = tid >> 5;
+        leaf_pair0_all(reinterpret_cast<double*>(S), t0, jb, w8, tid & 31);
+        __syncthreads();
+        if (J == 0) GPK_DBG(10);
+        if (w8 != 0 && w8 != 4) {
+          const int wi = w8 < 4 ? w8 - 1 : w8 - 2;  // 0..5
+          for (int u = wi; u < 2 * (npairs - 1); u += 6) {
+            const int pr = 1 + (u >> 1);
+            int rbk = 0, rem = pr;
+            while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
+            leaf_pair_half(reinterpret_cast<double*>(S), t0 + rbk * 32, t0 + rem * 32, jb, u & 1, tid & 31);
           }
-        if (grp == 0) break;              // warps 0-1 go on to the next diagonal block
-        pr = pr < 4 ? 3 + grp : pr + 3;   // the other three groups share the remaining pairs
+        }
+      } else {
+        // fp32: 64 threads (8x8 interleaved 4x4 micro-tiles) per pair; pair 0 = the next diagonal block, done by warps 0-1 only
+        const int sub = tid & 63;
+        int pr = grp;
+        while (pr < npairs) {
+          int rbk = 0, rem = pr;
+          while (rem > rbk) { rem -= rbk + 1; ++rbk; }  // pr -> (rbk, cbk = rem), cbk <= rbk
+          const int cbk = rem;
+          const int R0 = t0 + rbk * 32, C0 = t0 + cbk * 32;
+          leaf_pair_update(S, R0, C0, jb, sub);
+          if (grp == 0) break;              // warps 0-1 go on to the next diagonal block
+          pr = pr < 4 ? 3 + grp : pr + 3;   // the other three groups share the remaining pairs
+        }
+        if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");  // the next diagonal block is up to date
+        if (J == 0) GPK_DBG(10);
       }
-      if (grp == 0) asm volatile("bar.sync 1, 64;" ::: "memory");  // the next diagonal block is up to date
     }
     if (__all_sync(0xffffffffu, tid < 32)) {  // warp-uniform by construction: the vote tells the compiler so
       const int bad = warp_chol32<T>(S, t0, ldiag);
       if (bad && tid == 0 && info) atomicCAS(info, 0, info_base + t0 + bad);
+      if (J == 0) GPK_DBG(11);
     }
     __syncthreads();
     if (J == -1) { GPK_DBG(2); GPK_DBG(3); }
@@ -476,11 +652,6 @@ constexpr int PR = 64;    // panel rows per CTA
 constexpr int PLB = 132;  // row stride of the staged panel rows (= 4 mod 16: minimal-wavefront fragment loads)
 constexpr int PLW = 68;   // row stride of the 64-wide operands
 
-__device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
 
 // Optional extras of the panel kernel (both off = the plain solve):
 //  * PanelEmit: the finished rows are also written as int8 digit planes into the plane store (planes.cuh), with the

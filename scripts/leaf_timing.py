@@ -14,5 +14,6 @@ for rep in range(3):
     names = ["load", "chol32(J0)", "inv32(J0)", "panel(J0)", "trailing(J0)", "rest J1-3", "store L", "inv offdiag", "write dinv"]
     d = np.diff(t[:10])
     print("total cycles", t[9] - t[0], {n: int(v) for n, v in zip(names, d)})
+    print("   J0 detail: pair0 update", t[10] - t[4], "chol32(block 1)", t[11] - t[10], "wait for the other warps", t[5] - t[11])
 L = np.linalg.cholesky(K)
 print("err L", np.abs(np.tril(Kd.cpu().numpy()) - L).max(), "err inv", np.abs(dinv.cpu().numpy() - np.linalg.inv(L)).max())
