@@ -1052,6 +1052,37 @@ static int num_sms() {
   return n;
 }
 
+// Polling panel kernels are only safe while no OTHER factorisation competes for the SMs with polling kernels of its own
+// (four models on four streams: 4 x 64 polling CTAs fill the GPU and lock every leaf out).  One factorisation per device
+// may poll at a time: a factorisation enqueued while the previous one on a different stream is still in flight keeps
+// the event-ordered launches, whose only spinning kernels are single-CTA leaves.
+struct FlightReg { cudaEvent_t ev = nullptr; cudaStream_t stream = nullptr; bool valid = false; };
+static std::mutex g_flight_mu;
+static std::map<int, FlightReg> g_flight;
+
+// (both under g_flight_mu, which potrf_t holds from the check to the mark: the enqueue of one factorisation, ~1 ms of host time)
+static bool flight_alone(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = g_flight.find(dev);
+  if (it == g_flight.end() || !it->second.valid || it->second.stream == st) return true;
+  const cudaError_t q = cudaEventQuery(it->second.ev);
+  if (q == cudaSuccess) return true;
+  cudaGetLastError();  // (cudaErrorNotReady is not an error here)
+  return false;
+}
+
+static int flight_mark(cudaStream_t st) {
+  int dev = 0;
+  GPK_CUDA_OK(cudaGetDevice(&dev));
+  FlightReg& r = g_flight[dev];
+  if (!r.ev) GPK_CUDA_OK(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+  GPK_CUDA_OK(cudaEventRecord(r.ev, st));
+  r.stream = st;
+  r.valid = true;
+  return 0;
+}
+
 static bool flaghop_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPK_FLAG_HOPS"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1194,11 +1225,12 @@ static int potrf_block(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info
   }
   if (la.flaghop) {
     // The panel CTAs (one per SM: shared memory) spin until the leaf has finished, so the leaf must be able to get an SM
-    // whatever the block scheduler does first: only grids that leave two SMs free may poll; a larger grid (N > ~9000) is
-    // ordered behind the leaf by an event, as a launch boundary would.
+    // whatever the block scheduler does first: only grids that leave eight SMs free may poll (this leaf + the spinning
+    // leaves of factorisations enqueued later on other streams, which never poll themselves: potrf_t); a larger grid
+    // (N > ~9000) is ordered behind the leaf by an event, as a launch boundary would.
     const int64_t prow = rows - n;
     const int64_t ctas = fuse_cols > 0 ? (fuse_cols + PCR - 1) / PCR + (prow + PR - 1) / PR : (prow + PR - 1) / PR;
-    if (ctas <= num_sms() - 2) {
+    if (ctas <= num_sms() - 8) {
       em.leaf_flag = la.flag + 3;
       em.leaf_target = la.leaves_done;
     } else {
@@ -1323,7 +1355,9 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
   if (la.enabled) GPK_CUDA_OK(cudaMemsetAsync(la.flag, 0, 4 * sizeof(int), st));  // counters run up from here (la.base1 / base2)
   la.slim = sizeof(T) == 8 && n > NB && slim_enabled();
   la.fuse = la.slim && la.enabled && fuse_enabled();
-  la.flaghop = la.slim && la.enabled && flaghop_enabled();
+  std::unique_lock<std::mutex> flight_lock(g_flight_mu, std::defer_lock);
+  if (la.enabled) flight_lock.lock();
+  la.flaghop = la.slim && la.enabled && flaghop_enabled() && flight_alone(st);
   // digit-plane store for the tcgen05 trailing updates: fp64, slim panels (they emit the planes), n >= 2 tc_min_k
   const int S = pick_slices(cond_hint);
   if (sizeof(T) == 8) g_last_slices = 0;
@@ -1337,6 +1371,7 @@ int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, 
     GPK_CUDA_OK(cudaEventRecord(la.ev_side, la.side));
     GPK_CUDA_OK(cudaStreamWaitEvent(st, la.ev_side, 0));
   }
+  if (la.enabled) GPK_TRY(flight_mark(st));
   // slim leaves left only the 64x64 diagonal inverses: the full 128x128 block inverses that gpk_trsm consumes are
   // computed now, all blocks in parallel, off the factorisation's critical path (skipped when nobody will use them)
   if (la.slim && need_dinv) GPK_TRY(trtri_diag_t<T>(A, n, lda, dinv, st));

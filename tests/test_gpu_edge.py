@@ -123,3 +123,29 @@ def test_single_column_mean_broadcasts_over_outputs(cuda_device):
     np.testing.assert_allclose(mean.cpu().numpy(), mo + 0.5, rtol=1e-8, atol=1e-9)
     with pytest.raises(ValueError):
         ops.axpby(1.0, ops.to_device(np.zeros((5, 2))), 1.0, ops.to_device(np.zeros((5, 3))))
+
+
+def test_concurrent_factorisations_on_four_streams(cuda_device):
+    """Four GPR models evaluated on four CUDA streams (bench.py's independent-outputs arm of BASELINE configs[4]): the panel
+    kernels of only ONE factorisation at a time may poll their leaf's completion counter (potrf.cu::potrf_t) -- four
+    grids of polling CTAs would fill the GPU and lock the leaves out.  Values must equal the one-at-a-time results."""
+    import torch
+    models, ref = [], []
+    for i in range(4):
+        d = O.make_data(20 + i, 4096, 8, 1)
+        m = gpf.models.GPR((d["X"], d["Y"]), gpf.kernels.Matern52(lengthscales=2.0 + 0.3 * i), noise_variance=0.1)
+        models.append(m)
+        ref.append(float(m.log_marginal_likelihood()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in models]
+    cur = torch.cuda.current_stream()
+    for _ in range(3):
+        vals = []
+        for m, s_ in zip(models, streams):
+            s_.wait_stream(cur)
+            with torch.cuda.stream(s_):
+                vals.append(m.log_marginal_likelihood())
+        for s_ in streams:
+            cur.wait_stream(s_)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose([float(v) for v in vals], ref, rtol=1e-12)
