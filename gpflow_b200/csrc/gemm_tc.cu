@@ -3,16 +3,17 @@
 //     C[m, n]  -=  A[m, K] * A[0:n, K]^T          (row-major fp64; the Cholesky trailing update)
 //
 // tcgen05.mma has no f64 kind (f16/tf32/f8f6f4/i8/mx* only), so the fp64 operands are split into
-// signed 7-bit digits with a per-row power-of-two scale (an Ozaki-style error-free splitting):
+// balanced base-256 digits with a per-row power-of-two scale (an Ozaki-style splitting, planes.cuh):
 //
-//     a_ik = 2^(e_i - 6) * sum_s 2^(-7 s) d_s(i,k),   d_s in [-64, 64]  (int8),  s = 0..S-1
+//     a_ik = 2^(e_i - 6) * sum_s 2^(-8 s) d_s(i,k),   d_0 in [-65, 65], d_s in [-128, 127]  (int8),  s = 0..S-1
 //
 // The digit products accumulate EXACTLY in int32 on the tensor cores (kind::i8); products with the
-// same weight s+t = g share one TMEM accumulator, so a CTA tile (128 x 64) holds S accumulators of
-// 64 columns (S = 7 -> 448 of the 512 TMEM columns) and issues S(S+1)/2 MMAs per 32-deep k-step.
-// The epilogue converts the S integer planes to fp64, recombines them with exact power-of-two
-// weights and the row/column scales, and applies C -= ... .  Truncation error per dot product is
-// bounded by K * S * 2^(-7S) relative to the row maxima (S = 7: ~2^-46 * K/64).
+// same weight s+t = g < S share one TMEM accumulator.  S = 6 adds the (3,3) product in a seventh accumulator (the only
+// dropped term whose mean on the diagonal of C is not zero), so a CTA tile (128 x 64) holds 7 accumulators of 64 columns
+// (448 of the 512 TMEM columns) at S = 6 and S = 7 alike and issues 22 / 28 digit products per 32-deep k-step in 8 / 10
+// concatenated MMAs.  The epilogue converts the integer planes to fp64, recombines them with exact power-of-two
+// weights and the row/column scales, and ADDS the update into C with bulk reductions.  Error per dot product:
+// ~K * (S + 1) * 2^(-8S + 2) relative to the row scales from the dropped products (tests/test_digit_slicing_model.py).
 //
 // Pipeline (per persistent CTA, 192 threads):
 //   warp 0   producer : cp.async.bulk (1-D TMA) of PRE-TILED digit planes global -> shared, mbarrier

@@ -327,7 +327,7 @@ GPK_API int gpk_prof_read2(double* ms, int64_t* launches, double* work, int n);
  * The roofline denominators bench.py reports for syrk_i8_kernel and the DMMA kernels. */
 GPK_API int gpk_peak_probe(double* out_host, void* stream);
 /* Digit planes S used by the tcgen05 trailing updates of the most recent fp64 factorisation on this process (chosen from
- * the conditioning hint of the caller: 7, 8, or 0 = the updates ran on fp64 DMMA). */
+ * the conditioning hint of the caller: 6 or 7 base-256 planes; 0 = no update ran on tcgen05, e.g. n < 512 or fp32). */
 GPK_API int gpk_potrf_last_slices(void);
 /* Eager creation of the library-owned per-(device, stream) resources (see "Conventions"): the look-ahead side stream and
  * events, and `tf32_scratch_bytes` of TF32 plane scratch (0 = skip; 2 * 4 * (m + n) * k bytes cover an m x n x k product). */
