@@ -156,7 +156,7 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
   int bad = 0;
   T my_inv = T(1), my_diag = T(1);
 #ifndef GPK_CHOL32_VARIANT
-#define GPK_CHOL32_VARIANT 1  // measured on B200: 8.6k cycles per block (variant 0: 9.4k, variant 2: 9.8k)
+#define GPK_CHOL32_VARIANT 1  // measured on B200, cycles per block: variant 1 8.1k, variant 3 8.4k, variant 0 9.4k, variant 2 9.8k
 #endif
 #if GPK_CHOL32_VARIANT == 0
   // Right-looking, fully unrolled.  Alternatives measured (scripts/chol32_variants.sh): 8-column blocking and
@@ -198,6 +198,42 @@ __device__ __forceinline__ int warp_chol32(T* S, int jb, T* ldiag) {
     }
     if (j >= 1) a[j] = fma(-a[j - 1], __shfl_sync(0xffffffffu, a[j - 1], j), a[j]);
     T d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > T(0))) {
+      if (bad == 0) bad = j + 1;
+      d = T(1);
+    }
+    const T inv = rsqrt_t<T>(d);
+    if (lane == j) { my_inv = inv; my_diag = d * inv; }
+    a[j] *= inv;
+  }
+#elif GPK_CHOL32_VARIANT == 3
+  // variant 1 with ONE shuffle on the pivot chain instead of two: every lane forms the pivot d_j = A_jj - sum_k l_jk^2
+  // itself from the row-j entries it receives for the dot product anyway (same products, same summation order as lane
+  // j's own diagonal entry: bit-identical pivots), A_jj is a broadcast load from the still untouched shared block.
+  // Measured 3 % SLOWER than variant 1: the 496 extra DFMAs cost more issue slots than the shuffle latency they remove.
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    T dd = S[(jb + j) * LS + jb + j];
+    if (j >= 2) {
+      T p0 = T(0), p1 = T(0), p2 = T(0), p3 = T(0), s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < j - 1) {
+          const T ljk = __shfl_sync(0xffffffffu, a[k], j);
+          if ((k & 3) == 0) { p0 = fma(a[k], ljk, p0); s0 = fma(ljk, ljk, s0); }
+          else if ((k & 3) == 1) { p1 = fma(a[k], ljk, p1); s1 = fma(ljk, ljk, s1); }
+          else if ((k & 3) == 2) { p2 = fma(a[k], ljk, p2); s2 = fma(ljk, ljk, s2); }
+          else { p3 = fma(a[k], ljk, p3); s3 = fma(ljk, ljk, s3); }
+        }
+      a[j] -= (p0 + p1) + (p2 + p3);
+      dd -= (s0 + s1) + (s2 + s3);
+    }
+    if (j >= 1) {
+      const T l = __shfl_sync(0xffffffffu, a[j - 1], j);
+      a[j] = fma(-a[j - 1], l, a[j]);
+      dd = fma(-l, l, dd);
+    }
+    T d = dd;
     if (!(d > T(0))) {
       if (bad == 0) bad = j + 1;
       d = T(1);
@@ -697,6 +733,10 @@ potrf_panel_kernel(double* __restrict__ B, int64_t ldb, int64_t rows, const doub
   const int64_t r0 = critical ? (int64_t)blockIdx.x * PCR : (int64_t)ncrit * PCR + (int64_t)(blockIdx.x - ncrit) * PR;
   const bool wact = w * 8 < nrows_cta;  // warps beyond the CTA's rows only help with the cooperative loads / emission
   const int trace_id = fu.C ? 2 : 3;
+  // programmatic dependent launch (experiment, GPK_TC_PDL=1): the tcgen05 update behind a plain panel is then launched with
+  // the stream-serialisation attribute and blocks in griddepcontrol.wait until this grid has completed.  Measured 1 %
+  // slower per evaluation: the early-resident update CTAs take the free SMs and the next leaf starts late.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0 && blockIdx.x == 0) trace_mark(trace_id, 0);
   double* Bw = Bs + (w * 8) * PLB;  // this warp's 8 rows
   // Operands (A^-1, D^-1, C: 3 x 32 KB) and the CTA's rows (up to 64 KB) come in as 16-byte asynchronous copies, all in
@@ -1041,15 +1081,11 @@ static bool lookahead_enabled() {
   return v == 1;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+static int num_sms() {  // of the CURRENT device (a process may drive several)
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 }
 
 // Polling panel kernels are only safe while no OTHER factorisation competes for the SMs with polling kernels of its own

@@ -312,7 +312,7 @@ GPK_API void gpk_launch_count_reset(void);
  * the tensor pipe, padding tiles included). */
 #define GPK_PROF_CLASSES 8
 /* Tuning aid: runs ONE fp64 128x128 leaf (factor+invert) and stores clock64() at its phase
- * boundaries into dbg[0..9] (device int64). */
+ * boundaries into dbg[0..11] (device int64, at least 12 entries; scripts/leaf_timing.py names them). */
 GPK_API int gpk_debug_leaf(void* A, int64_t lda, int n, void* dinv, void* dbg, void* stream);
 /* Tuning aid: device timeline of a factorisation.  While `buf` is set, thread 0 of selected CTAs of the leaf (id 1), fused
  * panel (2), plain panel (3) and tcgen05 update (4) kernels append (%globaltimer ns, id << 8 | phase) pairs to buf[2 * capacity]

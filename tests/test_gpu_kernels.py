@@ -192,6 +192,41 @@ def test_potrf_panel_grid_larger_than_the_gpu(cuda_device):
     assert_allclose(2.0 * np.log(np.diag(Ln)).sum(), logdet, rtol=1e-11)
 
 
+def test_debug_trace_records_the_chain_of_a_factorisation(cuda_device):
+    """gpk_debug_trace: %globaltimer marks of the leaf / panel / update kernels of one factorisation (n = 1024: 8 leaves,
+    4 fused + 3 plain panels, 3 tcgen05 updates); switching it off stops the recording; the factor is unaffected."""
+    import ctypes
+    import torch
+    from gpflow_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(13)
+    n = 1024
+    K = _spd(n, rng, np.float64)
+    ref = sla.cholesky(K, lower=True)
+    cap = 512
+    buf = torch.zeros(2 * cap, dtype=torch.int64, device="cuda")
+    pos = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.gpk_debug_trace(ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(pos.data_ptr()), cap) == 0
+    try:
+        L, _ = ops.cholesky(ops.to_device(K))
+        torch.cuda.synchronize()
+    finally:
+        assert lib.gpk_debug_trace(None, None, 0) == 0
+    assert_allclose(to_np(L), ref, rtol=1e-10, atol=1e-11)
+    nmarks = int(pos.item())
+    assert 0 < nmarks <= cap
+    b = buf.cpu().numpy()[: 2 * nmarks].reshape(nmarks, 2)
+    kid, phase = b[:, 1] >> 8, b[:, 1] & 255
+    assert np.sum((kid == 1) & (phase == 0)) == 8 and np.sum((kid == 1) & (phase == 2)) == 8      # leaves: started, done
+    assert np.sum((kid == 2) & (phase == 0)) == 4 and np.sum((kid == 3) & (phase == 0)) >= 3      # fused / plain panels
+    assert np.sum((kid == 4) & (phase == 0)) == 3                                                    # K = 256, 512, 256
+    t = b[:, 0]
+    assert t.max() - t.min() < 50_000_000                                                            # one factorisation: << 50 ms
+    ops.cholesky(ops.to_device(K))
+    torch.cuda.synchronize()
+    assert int(pos.item()) == nmarks                                                                 # off: nothing appended
+
+
 def test_potrf_reports_non_positive_definite(cuda_device):
     rng = np.random.default_rng(10)
     n = 200
