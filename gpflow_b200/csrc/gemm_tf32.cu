@@ -49,6 +49,13 @@ __device__ __forceinline__ float to_tf32(float x) {
 //   trans = 0: src[r * ld + k]     trans = 1: src[k * ld + r]
 //   tri   = 1: the STORED matrix is lower triangular (band_part(-1,0)); entries with stored col > row read as 0
 // ------------------------------------------------------------------------------------------------
+// Index arithmetic without 64-bit divisions (the 1-D form of round 1 spent most of its time in them: 2.0 of the 7.5 ms of
+// BASELINE configs[2] went to this pre-pass) and whole-line stores in both orientations:
+//   trans = 0 (k contiguous in the source): a warp takes 8 rows x one 16-k tile column -- 8 x 64 B segments in, and the 4 core
+//     matrices of those 8 rows (512 contiguous bytes of the tile image) out; block = 8 consecutive k-blocks, grid.(y,z) = row groups
+//   trans = 1 (r contiguous): consecutive lanes walk r (coalesced loads, 128-byte runs of the core matrices out);
+//     block = 256 consecutive rows, grid.(y,z) = k-chunks
+constexpr int TF_SPLIT_YMAX = 32768;
 template <int RB>
 __global__ void __launch_bounds__(256)
 split_tiles_kernel(const float* __restrict__ src, int64_t R, int64_t K, int64_t ld, int trans, int tri,
@@ -58,23 +65,40 @@ split_tiles_kernel(const float* __restrict__ src, int64_t R, int64_t K, int64_t 
   // one thread = one 16-byte k-chunk (4 consecutive k) of one row
   const int64_t Rpad = (R + RB - 1) / RB * RB;
   const int64_t nchunk = KBn * 4;  // k-chunks per row
+  const int64_t slow = (int64_t)blockIdx.z * TF_SPLIT_YMAX + blockIdx.y;
   int64_t r, kc;
-  const int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (!trans) { kc = gid % nchunk; r = gid / nchunk; }          // consecutive threads walk k (contiguous)
-  else { r = gid % Rpad; kc = gid / Rpad; }                     // consecutive threads walk r (contiguous)
+  if (!trans) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    r = slow * 8 + (lane & 7);
+    kc = ((int64_t)blockIdx.x * 8 + w) * 4 + (lane >> 3);
+  } else {
+    r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    kc = slow;
+  }
   if (r >= Rpad || kc >= nchunk) return;
-  float v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t k = kc * 4 + q;
-    float x = 0.f;
-    if (r < R && k < K) {
-      const int64_t rl = rows_per_batch > 0 ? r % rows_per_batch : r;
-      const float* sb = rows_per_batch > 0 ? src + (r / rows_per_batch) * batch_stride : src;
-      const int64_t srow = trans ? k : rl, scol = trans ? rl : k;
-      if (!(tri && scol > srow)) x = sb[srow * ld + scol];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r < R) {
+    int64_t rl = r;
+    const float* sb = src;
+    if (rows_per_batch > 0) {
+      const int64_t bi = r / rows_per_batch;
+      rl = r - bi * rows_per_batch;
+      sb = src + bi * batch_stride;
     }
-    v[q] = x;
+    const int64_t k0 = kc * 4;
+    if (!trans && k0 + 3 < K && !tri && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(sb) & 15) == 0) {
+      const float4 t4 = *reinterpret_cast<const float4*>(sb + rl * ld + k0);
+      v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t k = k0 + q;
+        if (k < K) {
+          const int64_t srow = trans ? k : rl, scol = trans ? rl : k;
+          if (!(tri && scol > srow)) v[q] = sb[srow * ld + scol];
+        }
+      }
+    }
   }
   float hi[4], lo[4];
 #pragma unroll
@@ -82,11 +106,22 @@ split_tiles_kernel(const float* __restrict__ src, int64_t R, int64_t K, int64_t 
     hi[q] = to_tf32(v[q]);
     lo[q] = to_tf32(v[q] - hi[q]);
   }
-  const int64_t rb = r / RB, kb = kc / 4;
-  const int rr = (int)(r % RB), kk = (int)(kc % 4) * 4;
+  const int64_t rb = r / RB, kb = kc >> 2;   // (RB is a power of two: shifts)
+  const int rr = (int)(r % RB), kk = (int)(kc & 3) * 4;
   char* base = reinterpret_cast<char*>(tiles) + ((size_t)(rb * KBn + kb) * 2) * (RB * TF_KS * 4) + tf_tile_off(rr, kk);
   *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<float4*>(base + RB * TF_KS * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int RB>
+static void split_tiles_launch(const float* src, int64_t R, int64_t K, int64_t ld, int trans, int tri, float* tiles, int64_t KBn,
+                               int64_t rows_per_batch, int64_t batch_stride, cudaStream_t st) {
+  const int64_t Rpad = (R + RB - 1) / RB * RB;
+  const int64_t fast = trans ? (Rpad + 255) / 256 : (KBn + 7) / 8;
+  const int64_t slow = trans ? KBn * 4 : Rpad / 8;
+  const dim3 grid((unsigned)fast, (unsigned)(slow < TF_SPLIT_YMAX ? slow : TF_SPLIT_YMAX),
+                  (unsigned)((slow + TF_SPLIT_YMAX - 1) / TF_SPLIT_YMAX));
+  split_tiles_kernel<RB><<<grid, 256, 0, st>>>(src, R, K, ld, trans, tri, tiles, KBn, rows_per_batch, batch_stride);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -432,14 +467,11 @@ int gemm_tf32(int transa, int transb, int64_t m, int64_t n, int64_t k, float alp
   {
     ProfScope ps(PROF_MISC, st);
     // op(A) is [m, k]: stored [m,k] (transa = 0, k contiguous) or [k,m] (transa = 1)
-    const int64_t tot_a = mpad * KB * 4;
-    split_tiles_kernel<TF_BM><<<(unsigned)((tot_a + 255) / 256), 256, 0, st>>>(A, m, k, lda, transa ? 1 : 0,
-                                                                               (flags & GPK_GEMM_A_LOWER) ? 1 : 0, At, KB,
-                                                                               batch > 1 ? m_per : 0, a_batch_stride);
+    split_tiles_launch<TF_BM>(A, m, k, lda, transa ? 1 : 0, (flags & GPK_GEMM_A_LOWER) ? 1 : 0, At, KB, batch > 1 ? m_per : 0,
+                              a_batch_stride, st);
     GPK_LAUNCH_OK();
     // op(B)^T is [n, k]: stored [n,k] (transb = 1) or [k,n] (transb = 0 -> read transposed)
-    const int64_t tot_b = npad * KB * 4;
-    split_tiles_kernel<TF_BN><<<(unsigned)((tot_b + 255) / 256), 256, 0, st>>>(B, n, k, ldb, transb ? 0 : 1, 0, Bt, KB, 0, 0);
+    split_tiles_launch<TF_BN>(B, n, k, ldb, transb ? 0 : 1, 0, Bt, KB, 0, 0, st);
     GPK_LAUNCH_OK();
   }
   const int lower = (flags & GPK_GEMM_LOWER_ONLY) ? 1 : 0;
