@@ -112,3 +112,64 @@ def test_heteroskedastic_gaussian_bookkeeping():
     assert not gpf.likelihoods.Gaussian(0.3).heteroskedastic
     with pytest.raises(AssertionError):
         gpf.likelihoods.Gaussian(0.1, scale=0.2)
+
+
+# ---- mirror of the launch sequence of csrc/potrf.cu (potrf_rec / potrf_block / trailing_update, slim fp64 path) -------------
+def _potrf_schedule(n, rows, nb=128, tc_min_k=256):
+    """Returns the launch list of one factorisation as tuples; `follow` is threaded through the recursion exactly as the
+    (fk0, fK) arguments of potrf_rec: the k-range of the tcgen05 update that directly follows a sub-factorisation."""
+    out = []
+
+    def split_point(m):
+        return ((m // nb + 1) // 2) * nb
+
+    def eligible(m, nn, K):
+        return K >= tc_min_k and K % 32 == 0 and nn <= m
+
+    def block(n_, rows_, col0, fuse_cols, follow):
+        out.append(("leaf", col0))
+        if rows_ <= n_:
+            return
+        if fuse_cols > 0:
+            out.append(("fused_panel", col0, fuse_cols))
+            return
+        dyn = None
+        fk0, fK = follow
+        if n_ == nb and fK > 0 and fk0 + fK == col0 + n_ and rows_ + col0 > n:   # extra rows below the square part exist
+            dyn = (fk0, fK)
+        out.append(("panel", col0, dyn))
+
+    def rec(n_, rows_, col0, follow):
+        if n_ <= nb:
+            return block(n_, rows_, col0, 0, follow)
+        n1 = split_point(n_)
+        if n_ <= 2 * nb:
+            block(n1, rows_, col0, n_ - n1, (-1, 0))
+            return rec(n_ - n1, rows_ - n1, col0 + n1, follow)
+        tc = eligible(rows_ - n1, n_ - n1, n1)
+        rec(n1, rows_, col0, (col0, n1 if tc else 0))
+        out.append(("update", col0, n1, tc))
+        rec(n_ - n1, rows_ - n1, col0 + n1, follow)
+
+    rec(n, rows, 0, (-1, 0))
+    return out
+
+
+@pytest.mark.parametrize("n,extra", [(8192, 1), (4096, 3), (1024, 0), (1536, 2), (8192 + 128, 1), (700, 1)])
+def test_every_tcgen05_update_finds_its_extra_rows_sliced_by_the_panel_before_it(n, extra):
+    sched = _potrf_schedule(n, n + extra)
+    leaves = [e[1] for e in sched if e[0] == "leaf"]
+    assert leaves == list(range(0, n, 128))                                   # one leaf per diagonal block, in order
+    for i, e in enumerate(sched):
+        if e[0] == "update" and e[3]:                                         # runs on tcgen05
+            prev = sched[i - 1]
+            assert prev[0] == "panel" and prev[1] + 128 == e[1] + e[2]        # a PLAIN panel, the block that ends the k-range
+            if extra and prev[1] + 128 <= n:
+                assert prev[2] == (e[1], e[2])                                # ... which sliced [col0, col0 + K) for it
+        if e[0] == "panel" and e[2] is not None:
+            nxt = sched[i + 1]
+            assert nxt[0] == "update" and (nxt[1], nxt[2]) == e[2]            # never a stale k-range
+        if e[0] == "fused_panel":
+            assert sched[i + 1][0] == "leaf"                                  # the fused update plays the role of U
+    if n == 8192:
+        assert sum(e[0] == "update" for e in sched) == 31 and sum(e[0] == "fused_panel" for e in sched) == 32
