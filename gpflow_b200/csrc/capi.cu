@@ -53,7 +53,7 @@ int potrf_any(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t*
   void* tcws = tcb ? (char*)ws + align_up(dinv_bytes(n, dtype), 256) + 256 : nullptr;
   if (dtype == GPK_F64)
     return potrf_t<double>((double*)A, n, rows, lda, info, (double*)ws, tcws, tcb, st, need_dinv, cond_hint);
-  return potrf_t<float>((float*)A, n, rows, lda, info, (float*)ws, nullptr, 0, st, need_dinv);
+  return potrf_t<float>((float*)A, n, rows, lda, info, (float*)ws, tcws, tcb, st, need_dinv);
 }
 
 int trsm_any(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t nrhs, int64_t ldb, int dtype,

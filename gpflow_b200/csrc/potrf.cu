@@ -1200,8 +1200,31 @@ static int trailing_update(T* C, int64_t ldc, int64_t m, int64_t n, const T* P, 
   return rc;
 }
 
+// (fp32 factorisations by way of the fp64 path: potrf_f32_via_f64 below)
+static bool f32_via_f64_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPK_F32_VIA_F64"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static bool f32_detour_applies(int64_t n, int64_t rows) { return rows <= n && n >= 512 && n <= 65535 && f32_via_f64_enabled(); }
+struct F32Detour { int64_t ld64; size_t a_bytes, d_bytes, p_bytes; };
+static F32Detour f32_detour_layout(int64_t n) {
+  F32Detour d;
+  d.ld64 = (n + 3) / 4 * 4;
+  d.a_bytes = align_up((size_t)n * d.ld64 * sizeof(double), 256);
+  d.d_bytes = align_up((size_t)((n + NB - 1) / NB) * NB * NB * sizeof(double) + 256, 256);
+  d.p_bytes = align_up(tc_planes_bytes(n, n), 256);
+  return d;
+}
+
 size_t potrf_tc_ws_bytes(int64_t n, int64_t rows, int dtype) {
-  if (dtype != GPK_F64 || n < 2 * 128) return 0;  // sized for any GPK_TC_MIN_K >= 128
+  if (dtype == GPK_F32) {  // scratch of the fp64 detour of square fp32 factorisations (potrf_f32_via_f64)
+    if (!f32_detour_applies(n, rows)) return 0;
+    const F32Detour L = f32_detour_layout(n);
+    return L.a_bytes + L.d_bytes + L.p_bytes;
+  }
+  if (n < 2 * 128) return 0;  // sized for any GPK_TC_MIN_K >= 128
   return tc_planes_bytes(n, rows);
 }
 
@@ -1378,10 +1401,52 @@ static int pick_slices(double cond_hint) {
   return (cond_hint > 0.0 && cond_hint <= 1e4) ? 6 : 7;
 }
 
+// ---- fp32 factorisations by way of the fp64 path --------------------------------------------------------------------------
+// The fp32 factorisation keeps the round-1 structure (full-inverse leaf, 63-70 us, panel solves and updates as CUDA-core
+// GEMMs): chol(Kuu) at M = 2048 costs ~1.8 ms of the 3.3 ms SVGP step.  The fp64 path (slim DMMA leaf, panel kernel, tcgen05
+// updates) factors the same matrix in ~1.0 ms, so a square fp32 matrix of n >= 512 is widened to fp64, factored there and
+// rounded back; the fp32 block inverses the triangular solves consume are recomputed from the rounded factor.  (The factor
+// is the correctly rounded fp64 factor instead of an fp32-accumulated one.)  The fp64 copy, its block-inverse slots and its
+// digit planes live in the CALLER's workspace: potrf_tc_ws_bytes(n, rows, GPK_F32) is part of gpk_potrf_ws / the fused
+// objectives' workspace queries.  GPK_F32_VIA_F64=0 keeps the fp32 kernels.
+__global__ void widen_lower_kernel(const float* __restrict__ A, int64_t lda, double* __restrict__ B, int64_t ldb, int64_t n) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c <= r && c < n) B[r * ldb + c] = (double)A[r * lda + c];
+}
+__global__ void narrow_lower_kernel(const double* __restrict__ B, int64_t ldb, float* __restrict__ A, int64_t lda, int64_t n) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c <= r && c < n) A[r * lda + c] = (float)B[r * ldb + c];
+}
+
+static int potrf_f32_via_f64(float* A, int64_t n, int64_t lda, int32_t* info, float* dinv, void* scratch, cudaStream_t st,
+                             bool need_dinv) {
+  const F32Detour L = f32_detour_layout(n);
+  char* ws = (char*)scratch;
+  double* A64 = (double*)ws;
+  double* dinv64 = (double*)(ws + L.a_bytes);
+  void* planes = ws + L.a_bytes + L.d_bytes;
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  {
+    ProfScope ps(PROF_MISC, st);
+    widen_lower_kernel<<<grid, 256, 0, st>>>(A, lda, A64, L.ld64, n);
+    GPK_LAUNCH_OK();
+  }
+  GPK_TRY(potrf_t<double>(A64, n, n, L.ld64, info, dinv64, planes, L.p_bytes, st, /*need_dinv=*/false, /*cond_hint=*/0.0));
+  {
+    ProfScope ps(PROF_MISC, st);
+    narrow_lower_kernel<<<grid, 256, 0, st>>>(A64, L.ld64, A, lda, n);
+    GPK_LAUNCH_OK();
+  }
+  if (need_dinv) GPK_TRY(trtri_diag_t<float>(A, n, lda, dinv, st));
+  return 0;
+}
+
 template <typename T>
 int potrf_t(T* A, int64_t n, int64_t rows, int64_t lda, int32_t* info, T* dinv, void* tcws, size_t tcws_bytes,
             cudaStream_t st, bool need_dinv, double cond_hint) {
   if (n <= 0) return 0;
+  if (sizeof(T) == 4 && f32_detour_applies(n, rows) && tcws && tcws_bytes >= potrf_tc_ws_bytes(n, rows, GPK_F32))
+    return potrf_f32_via_f64(reinterpret_cast<float*>(A), n, lda, info, reinterpret_cast<float*>(dinv), tcws, st, need_dinv);
   GPK_TRY(leaf_attr<T>());
   if (info) GPK_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
   LookAhead la;

@@ -105,8 +105,9 @@ GPK_API int gpk_kdiag(const gpk_knode* nodes, int n_nodes, const int32_t* dims, 
  * models/sgpr.py:201,207, conditionals/util.py:67, kullback_leiblers.py:107) and the
  * triangular_solve of logdensities.py:150.
  *   ws: gpk_potrf_ws(n, rows, dtype) bytes; on return its head holds the inverses of the 128x128
- *       diagonal blocks of L (reused by gpk_trsm via `dinv`); the rest is scratch for the int8
- *       digit planes of the tcgen05 trailing update (fp64, n >= 512).
+ *       diagonal blocks of L (reused by gpk_trsm via `dinv`); the rest is scratch: the int8 digit planes of the
+ *       tcgen05 trailing updates (fp64, n >= 256), or -- square fp32 matrices of n >= 512, which are widened,
+ *       factored on the fp64 path and rounded back -- the fp64 copy with its own inverse slots and planes.
  *   info (device int32, may be NULL): 0, or 1-based index of the first non-positive pivot. */
 GPK_API size_t gpk_potrf_ws(int64_t n, int64_t rows, int dtype);
 GPK_API int gpk_potrf(void* A, int64_t n, int64_t rows, int64_t lda, int dtype, int32_t* info, void* ws,
